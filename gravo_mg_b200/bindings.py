@@ -1,0 +1,280 @@
+"""The ``gravomg_bindings`` module surface, re-implemented over the C ABI.
+
+Mirrors the pybind11 module of the reference (gravomg_bindings/src/cpp/core.cpp:142-180):
+class ``MultigridSolver`` with the same 22 positional constructor arguments and the same
+methods, plus the enums ``Hierarchy``, ``Sampling`` and ``Weighting``. The reference's
+``gravomg/core.py`` runs unmodified on top of this module.
+
+Only the V-cycle path (``solve``, ``residual``, hierarchy accessors, timing writers) is
+implemented; ``direct_solve``, ``construct_sig21_hierarchy`` and ``toggle_hierarchy`` to a
+non-default hierarchy raise ``NotImplementedError`` (out of scope).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from ._lib import lib, check, i32, f64, as_i32, as_f64
+
+
+class Hierarchy(enum.IntEnum):
+    OURS = 0
+    SIG21 = 1
+
+
+class Sampling(enum.IntEnum):
+    FASTDISK = 0
+    POISSONDISK = 1
+    FPS = 2
+    RANDOM = 3
+    MIS = 4
+
+
+class Weighting(enum.IntEnum):
+    BARYCENTRIC = 0
+    UNIFORM = 1
+    INVDIST = 2
+
+
+def _csr_arrays(m):
+    """(indptr int32, indices int32, data f64) of a scipy matrix, converting to CSR if needed."""
+    if not sp.issparse(m):
+        raise TypeError("expected a scipy.sparse matrix")
+    m = m.tocsr()
+    if m.nnz >= 2**31:
+        raise ValueError("matrices with 2^31 or more stored entries are not supported")
+    return as_i32(m.indptr), as_i32(m.indices), as_f64(m.data)
+
+
+def _dense_rhs(a, n):
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        a = a[:, None]  # the Eigen caster loads a vector as N x 1; the result is always 2-D
+    if a.ndim != 2 or a.shape[0] != n:
+        raise ValueError(f"expected an array of shape ({n}, K), got {a.shape}")
+    return np.ascontiguousarray(a)
+
+
+def _fmt(v):
+    return "%g" % v  # std::ofstream's default formatting of a double
+
+
+class MultigridSolver:
+    def __init__(self, positions, neighbors, mass, ratio, low_bound, cycle_type, tolerance, stopping_criteria,
+                 pre_iters, post_iters, max_iter, check_voronoi, nested, sampling_strategy, weighting, sig06,
+                 normals, verbose, debug, ablation, ablation_num_points, ablation_random,
+                 *, omega=2.0 / 3.0, dtype="float64", device=0, build_hierarchy=True):
+        self._h = C.c_void_p()
+        pos = as_f64(positions)
+        if pos.ndim != 2 or pos.shape[1] != 3:
+            raise ValueError("positions must have shape (N, 3)")
+        neigh = as_i32(neighbors)
+        if neigh.ndim != 2 or neigh.shape[0] != pos.shape[0]:
+            raise ValueError("neighbors must have shape (N, max_neighbors)")
+        self._n = pos.shape[0]
+        p = _lib.GmgParams()
+        check(None, lib.gmg_default_params(C.byref(p)))
+        p.ratio, p.low_bound, p.cycle_type = float(ratio), int(low_bound), int(cycle_type)
+        p.tolerance, p.stopping_criteria = float(tolerance), int(stopping_criteria)
+        p.pre_iters, p.post_iters, p.max_iter = int(pre_iters), int(post_iters), int(max_iter)
+        p.check_voronoi, p.nested = int(bool(check_voronoi)), int(bool(nested))
+        p.sampling_strategy, p.weighting = int(sampling_strategy), int(weighting)
+        p.sig06, p.verbose, p.debug = int(bool(sig06)), int(bool(verbose)), int(bool(debug))
+        p.ablation, p.ablation_num_points, p.ablation_random = int(bool(ablation)), int(ablation_num_points), int(bool(ablation_random))
+        p.omega = float(omega)
+        p.dtype = {"float64": 0, "fp64": 0, "f64": 0, "float32": 1, "fp32": 1, "f32": 1}[str(np.dtype(dtype)) if not isinstance(dtype, str) else dtype]
+        p.device = int(device)
+        p.build_hierarchy = int(bool(build_hierarchy))
+        mp, mi, md = _csr_arrays(mass)
+        if mass.shape != (self._n, self._n):
+            raise ValueError("mass must be N x N")
+        check(None, lib.gmg_create(C.byref(p), self._n, f64(pos), i32(neigh), neigh.shape[1], i32(mp), i32(mi), f64(md), C.byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.gmg_destroy(h)
+            self._h = None
+
+    # ------------------------------------------------------------------ out of scope
+    def construct_sig21_hierarchy(self, F):
+        raise NotImplementedError("the SIG21 comparison hierarchy is outside the accelerated V-cycle path")
+
+    def toggle_hierarchy(self, hierarchy):
+        if int(hierarchy) != int(Hierarchy.OURS):
+            raise NotImplementedError("only Hierarchy.OURS exists in this implementation")
+
+    def direct_solve(self, lhs, rhs, pardiso):
+        raise NotImplementedError("direct_solve (Eigen LLT / Pardiso baselines) is outside the accelerated V-cycle path")
+
+    # ------------------------------------------------------------------ the hot path
+    def solve(self, lhs, rhs):
+        ap, ai, ad = _csr_arrays(lhs)
+        b = _dense_rhs(rhs, self._n)
+        x = np.empty_like(b)
+        check(self._h, lib.gmg_solve(self._h, self._n, i32(ap), i32(ai), f64(ad), f64(b), f64(x), b.shape[1]))
+        return x
+
+    def residual(self, lhs, rhs, solution, type=2):
+        ap, ai, ad = _csr_arrays(lhs)
+        b = _dense_rhs(rhs, self._n)
+        x = _dense_rhs(solution, self._n)
+        if x.shape != b.shape:
+            raise ValueError("rhs and solution must have the same shape")
+        out = C.c_double()
+        check(self._h, lib.gmg_residual(self._h, self._n, i32(ap), i32(ai), f64(ad), f64(b), f64(x), b.shape[1], int(type), C.byref(out)))
+        return out.value
+
+    # split form used by the benchmark to keep the system resident in HBM
+    def stage(self, lhs, rhs):
+        ap, ai, ad = _csr_arrays(lhs)
+        b = _dense_rhs(rhs, self._n)
+        self._staged_shape = b.shape
+        check(self._h, lib.gmg_stage_system(self._h, self._n, i32(ap), i32(ai), f64(ad), f64(b), b.shape[1]))
+
+    def solve_staged(self):
+        check(self._h, lib.gmg_solve_staged(self._h))
+
+    def fetch(self, out=None):
+        x = np.empty(self._staged_shape) if out is None else out
+        check(self._h, lib.gmg_fetch_solution(self._h, f64(x)))
+        return x
+
+    # ------------------------------------------------------------------ data access
+    def prolongation_matrices(self):
+        count = C.c_int32()
+        check(self._h, lib.gmg_num_levels(self._h, C.byref(count)))
+        out = []
+        for k in range(count.value):
+            rows, cols, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+            check(self._h, lib.gmg_prolongation_shape(self._h, k, C.byref(rows), C.byref(cols), C.byref(nnz)))
+            indptr = np.empty(rows.value + 1, dtype=np.int32)
+            indices = np.empty(nnz.value, dtype=np.int32)
+            data = np.empty(nnz.value, dtype=np.float64)
+            check(self._h, lib.gmg_get_prolongation(self._h, k, i32(indptr), i32(indices), f64(data)))
+            out.append(sp.csr_matrix((data, indices, indptr), shape=(rows.value, cols.value)).tocsc())  # Eigen hands back CSC
+        return out
+
+    def set_prolongation_matrices(self, U):
+        check(self._h, lib.gmg_clear_prolongations(self._h))
+        for k, u in enumerate(U):
+            up, ui, ud = _csr_arrays(u)
+            check(self._h, lib.gmg_set_prolongation(self._h, k, u.shape[0], u.shape[1], i32(up), i32(ui), f64(ud)))
+
+    def _level_arrays(self, fn, dtype, width=None):
+        count = C.c_int32()
+        check(self._h, lib.gmg_num_levels(self._h, C.byref(count)))
+        out = []
+        for k in range(count.value):
+            size = C.c_int64(0)
+            if fn(self._h, k, None, C.byref(size)) != 0:
+                break  # debug-only arrays are empty unless debug=True, as upstream
+            a = np.empty(size.value, dtype=dtype)
+            ptr = i32(a) if dtype == np.int32 else f64(a)
+            check(self._h, fn(self._h, k, ptr, C.byref(size)))
+            out.append(a.reshape(-1, width) if width else a)
+        return out
+
+    def sampling_indices(self):
+        return [a.tolist() for a in self._level_arrays(lib.gmg_get_samples, np.int32)]
+
+    def nearest_source(self):
+        return [a.tolist() for a in self._level_arrays(lib.gmg_get_nearest_source, np.int32)]
+
+    def level_points(self):
+        return self._level_arrays(lib.gmg_get_level_points, np.float64, 3)
+
+    def all_triangles(self):
+        return [a.tolist() for a in self._level_arrays(lib.gmg_get_all_triangles, np.int32, 3)]
+
+    def notrimap(self):
+        return [a.tolist() for a in self._level_arrays(lib.gmg_get_notrimap, np.int32)]
+
+    def level_edges(self):
+        return []  # never filled by the reference either (levelE is only declared)
+
+    def coarse_normals(self):
+        return []  # levelN is only filled by the ablation hierarchy upstream
+
+    # ------------------------------------------------------------------ timing / logs
+    def _timing(self, which):
+        buf = C.create_string_buffer(4096)
+        check(self._h, lib.gmg_timing_keys(self._h, which, buf, len(buf)))
+        keys = [k for k in buf.value.decode().split(",") if k]
+        out = {}
+        for k in keys:
+            v = C.c_double()
+            check(self._h, lib.gmg_get_timing(self._h, which, k.encode(), C.byref(v)))
+            out[k] = v.value
+        return out
+
+    def hierarchy_timing(self):
+        return self._timing(0)
+
+    def solver_timing(self):
+        return self._timing(1)
+
+    def convergence(self):
+        count = C.c_int32(0)
+        check(self._h, lib.gmg_get_convergence(self._h, None, None, C.byref(count)))
+        t = np.empty(count.value)
+        r = np.empty(count.value)
+        check(self._h, lib.gmg_get_convergence(self._h, f64(t), f64(r), C.byref(count)))
+        return list(zip(t.tolist(), r.tolist()))
+
+    def _write_timing(self, timing, experiment, file, write_headers):
+        # same layout as MGBS::writeTiming (gravomg/src/utility.cpp:106-131)
+        with open(file, "w" if write_headers else "a") as f:
+            if write_headers:
+                f.write("experiment" + "".join("," + k for k in timing) + "\n")
+            f.write(str(experiment) + "".join("," + _fmt(v) for v in timing.values()) + "\n")
+
+    def write_hierarchy_timing(self, experiment, file, write_headers):
+        self._write_timing(self.hierarchy_timing(), experiment, file, write_headers)
+
+    def write_solver_timing(self, experiment, file, write_headers):
+        self._write_timing(self.solver_timing(), experiment, file, write_headers)
+
+    def write_convergence(self, file):
+        # MGBS::writeConvergence (gravomg/src/utility.cpp:133-149)
+        with open(file, "w") as f:
+            f.write("time,residue\n")
+            for t, r in self.convergence():
+                f.write(f"{_fmt(t)},{_fmt(r)}\n")
+
+    # ------------------------------------------------------------------ options / measurement
+    def set_option(self, key, value):
+        check(self._h, lib.gmg_set_option(self._h, key.encode(), float(value)))
+
+    def get_option(self, key):
+        v = C.c_double()
+        check(self._h, lib.gmg_get_option(self._h, key.encode(), C.byref(v)))
+        return v.value
+
+    def level_info(self):
+        out = []
+        k = 0
+        while True:
+            rows, nnz_a, nnz_u = C.c_int64(), C.c_int64(), C.c_int64()
+            if lib.gmg_level_info(self._h, k, C.byref(rows), C.byref(nnz_a), C.byref(nnz_u)) != 0:
+                break
+            out.append({"rows": rows.value, "nnz_a": nnz_a.value, "nnz_u": nnz_u.value})
+            k += 1
+        return out
+
+    def kernel_profile(self, kind, level=-1):
+        ms, launches = C.c_double(), C.c_int64()
+        check(self._h, lib.gmg_kernel_profile(self._h, int(kind), int(level), C.byref(ms), C.byref(launches)))
+        return ms.value, launches.value
+
+    def reset_kernel_profile(self):
+        check(self._h, lib.gmg_reset_kernel_profile(self._h))
+
+    def last_launch_count(self):
+        v = C.c_int64()
+        check(self._h, lib.gmg_last_launch_count(self._h, C.byref(v)))
+        return v.value

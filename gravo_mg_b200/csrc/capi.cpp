@@ -1,0 +1,372 @@
+// extern "C" surface declared in include/gravomg_b200.h. Every entry point catches C++
+// exceptions and turns them into a status code plus gmg_last_error().
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <exception>
+#include <memory>
+#include <stdexcept>
+#include <string>
+
+#include "solver.h"
+
+using gmg::SolverState;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename F>
+int guarded(gmg_handle h, F&& body) {
+    try {
+        body();
+        return 0;
+    } catch (const std::exception& e) {
+        if (h)
+            h->s.error = e.what();
+        else
+            g_create_error = e.what();
+        return 1;
+    } catch (...) {
+        if (h)
+            h->s.error = "unknown error";
+        else
+            g_create_error = "unknown error";
+        return 1;
+    }
+}
+
+void require(bool ok, const char* msg) {
+    if (!ok) throw std::invalid_argument(msg);
+}
+
+gmg::EngineBase& engine(gmg_handle h) {
+    if (!h->s.engine) h->s.engine = gmg::make_engine(&h->s);
+    return *h->s.engine;
+}
+
+template <typename V>
+void copy_out(const V& src, typename V::value_type* out, int64_t* count) {
+    if (out) {
+        require(*count >= (int64_t)src.size(), "output buffer too small");
+        std::copy(src.begin(), src.end(), out);
+    }
+    *count = (int64_t)src.size();
+}
+
+}  // namespace
+
+extern "C" {
+
+int gmg_default_params(gmg_params* p) {
+    if (!p) return 1;
+    std::memset(p, 0, sizeof *p);
+    p->ratio = 8.0;
+    p->low_bound = 1000;
+    p->cycle_type = 0;
+    p->tolerance = 1e-4;
+    p->stopping_criteria = 2;
+    p->pre_iters = 2;
+    p->post_iters = 2;
+    p->max_iter = 100;
+    p->check_voronoi = 1;
+    p->nested = 0;
+    p->sampling_strategy = GMG_SAMPLING_FASTDISK;
+    p->weighting = GMG_WEIGHTING_BARYCENTRIC;
+    p->ablation_num_points = 3;
+    p->smoother = GMG_SMOOTHER_JACOBI;
+    p->omega = 2.0 / 3.0;
+    p->dtype = GMG_DTYPE_F64;
+    p->device = 0;
+    p->build_hierarchy = 1;
+    return 0;
+}
+
+int gmg_create(const gmg_params* p, int64_t n, const double* pos, const int32_t* neigh, int32_t kn,
+               const int32_t* m_indptr, const int32_t* m_indices, const double* m_data, gmg_handle* out) {
+    if (out) *out = nullptr;
+    return guarded(nullptr, [&] {
+        require(p && out, "null argument");
+        require(n > 0 && n < (int64_t)1 << 31, "number of points must be in (0, 2^31)");
+        require(pos && neigh && kn > 0, "positions and a padded neighbour array are required");
+        require(m_indptr && m_indices && m_data, "mass matrix is required");
+        require(p->sampling_strategy == GMG_SAMPLING_FASTDISK, "only Sampling.FASTDISK is implemented (the others are paper ablations)");
+        require(!p->sig06 && !p->ablation, "the SIG06 and ablation hierarchies are out of scope");
+        require(p->weighting >= 0 && p->weighting <= 2, "unknown weighting scheme");
+        require(p->smoother == GMG_SMOOTHER_JACOBI, "unknown smoother");
+        require(p->dtype == GMG_DTYPE_F64 || p->dtype == GMG_DTYPE_F32, "unknown dtype");
+        std::unique_ptr<gmg_solver> h(new gmg_solver());
+        SolverState& s = h->s;
+        s.params = *p;
+        s.n = n;
+        s.mass_diag.assign(n, 0.0);
+        for (int64_t i = 0; i < n; ++i) {
+            for (int q = m_indptr[i]; q < m_indptr[i + 1]; ++q) {
+                if (m_indices[q] == i)
+                    s.mass_diag[i] += m_data[q];
+                else
+                    require(m_data[q] == 0.0, "mass matrix must be diagonal (lumped), as every caller of the reference passes");
+            }
+        }
+        for (int64_t i = 0; i < n; ++i)
+            for (int j = 0; j < kn; ++j) require(neigh[i * kn + j] >= -1 && neigh[i * kn + j] < n, "neighbour index out of range");
+        if (p->build_hierarchy) {
+            gmg::HierarchyOptions o;
+            o.ratio = p->ratio, o.low_bound = p->low_bound, o.check_voronoi = p->check_voronoi != 0, o.nested = p->nested != 0;
+            o.weighting = p->weighting, o.debug = p->debug != 0, o.verbose = p->verbose != 0;
+            gmg::build_hierarchy(pos, n, neigh, kn, o, s.hier);
+        } else {
+            s.hier.dof.push_back(n);
+            s.hier.timing["n_vertices"] = (double)n;
+        }
+        *out = h.release();
+    });
+}
+
+void gmg_destroy(gmg_handle h) { delete h; }
+
+const char* gmg_last_error(gmg_handle h) { return h ? h->s.error.c_str() : g_create_error.c_str(); }
+
+int gmg_set_option(gmg_handle h, const char* key, double value) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(key != nullptr, "null key");
+        SolverState& s = h->s;
+        const std::string k(key);
+        bool cycle = false, hierarchy = false;
+        if (k == "tolerance") s.params.tolerance = value;
+        else if (k == "max_iter") s.params.max_iter = (int)value;
+        else if (k == "stopping_criteria") s.params.stopping_criteria = (int)value, cycle = true;
+        else if (k == "pre_iters") s.params.pre_iters = (int)value, cycle = true;
+        else if (k == "post_iters") s.params.post_iters = (int)value, cycle = true;
+        else if (k == "omega") s.params.omega = value, cycle = true;
+        else if (k == "cycle_type") s.params.cycle_type = (int)value;
+        else if (k == "use_graph") s.use_graph = value != 0.0;
+        else if (k == "loop_mode") s.loop_mode = (int)value;
+        else if (k == "profile") s.profile = value != 0.0;
+        else if (k == "kernel_path") s.kernel_path = (int)value, hierarchy = true;
+        else throw std::invalid_argument("unknown option: " + k);
+        require(s.params.pre_iters >= 0 && s.params.post_iters >= 0, "sweep counts must be >= 0");
+        if (s.engine && hierarchy) s.engine->invalidate_hierarchy();
+        if (s.engine && cycle) s.engine->invalidate_cycle();
+    });
+}
+
+int gmg_get_option(gmg_handle h, const char* key, double* value) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(key && value, "null argument");
+        const SolverState& s = h->s;
+        const std::string k(key);
+        if (k == "tolerance") *value = s.params.tolerance;
+        else if (k == "max_iter") *value = s.params.max_iter;
+        else if (k == "stopping_criteria") *value = s.params.stopping_criteria;
+        else if (k == "pre_iters") *value = s.params.pre_iters;
+        else if (k == "post_iters") *value = s.params.post_iters;
+        else if (k == "omega") *value = s.params.omega;
+        else if (k == "cycle_type") *value = s.params.cycle_type;
+        else if (k == "use_graph") *value = s.use_graph;
+        else if (k == "loop_mode") *value = s.loop_mode;
+        else if (k == "profile") *value = s.profile;
+        else if (k == "kernel_path") *value = s.kernel_path;
+        else throw std::invalid_argument("unknown option: " + k);
+    });
+}
+
+// ---- hierarchy ------------------------------------------------------------------------
+int gmg_num_levels(gmg_handle h, int32_t* n_prolongations) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(n_prolongations != nullptr, "null argument");
+        *n_prolongations = (int32_t)h->s.hier.U.size();
+    });
+}
+
+int gmg_prolongation_shape(gmg_handle h, int32_t level, int64_t* rows, int64_t* cols, int64_t* nnz) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(level >= 0 && level < (int)h->s.hier.U.size(), "level out of range");
+        const gmg::HostCsr& u = h->s.hier.U[level];
+        *rows = u.rows, *cols = u.cols, *nnz = u.nnz();
+    });
+}
+
+int gmg_get_prolongation(gmg_handle h, int32_t level, int32_t* indptr, int32_t* indices, double* data) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(level >= 0 && level < (int)h->s.hier.U.size(), "level out of range");
+        const gmg::HostCsr& u = h->s.hier.U[level];
+        std::copy(u.indptr.begin(), u.indptr.end(), indptr);
+        std::copy(u.indices.begin(), u.indices.end(), indices);
+        std::copy(u.data.begin(), u.data.end(), data);
+    });
+}
+
+int gmg_clear_prolongations(gmg_handle h) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        SolverState& s = h->s;
+        s.hier.U.clear();
+        s.hier.dof.assign(1, s.n);
+        if (s.engine) s.engine->invalidate_hierarchy();
+    });
+}
+
+int gmg_set_prolongation(gmg_handle h, int32_t level, int64_t rows, int64_t cols, const int32_t* indptr,
+                         const int32_t* indices, const double* data) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        SolverState& s = h->s;
+        require(level == (int)s.hier.U.size(), "prolongations must be set in order, after gmg_clear_prolongations");
+        require(rows == s.hier.dof.back(), "prolongation has the wrong number of rows for this level");
+        require(cols > 0 && indptr && indices && data, "invalid prolongation");
+        require(indptr[0] == 0, "indptr must start at 0");
+        gmg::HostCsr u;
+        u.rows = rows, u.cols = cols;
+        u.indptr.assign(indptr, indptr + rows + 1);
+        const int64_t nnz = indptr[rows];
+        for (int64_t r = 0; r < rows; ++r) require(indptr[r + 1] >= indptr[r], "indptr must be non-decreasing");
+        for (int64_t q = 0; q < nnz; ++q) require(indices[q] >= 0 && indices[q] < cols, "prolongation column index out of range");
+        u.indices.assign(indices, indices + nnz);
+        u.data.assign(data, data + nnz);
+        gmg::sort_rows_sum_duplicates(u);
+        s.hier.U.push_back(std::move(u));
+        s.hier.dof.push_back(cols);
+        if (s.engine) s.engine->invalidate_hierarchy();
+    });
+}
+
+#define GMG_LEVEL_GETTER(NAME, FIELD, TYPE)                                                        \
+    int NAME(gmg_handle h, int32_t level, TYPE* out, int64_t* count) {                             \
+        if (!h) return 1;                                                                          \
+        return guarded(h, [&] {                                                                    \
+            require(count != nullptr, "null argument");                                            \
+            require(level >= 0 && level < (int)h->s.hier.FIELD.size(), "level out of range (some arrays exist only with debug=True)"); \
+            copy_out(h->s.hier.FIELD[level], out, count);                                          \
+        });                                                                                        \
+    }
+GMG_LEVEL_GETTER(gmg_get_samples, samples, int32_t)
+GMG_LEVEL_GETTER(gmg_get_nearest_source, nearest_source, int32_t)
+GMG_LEVEL_GETTER(gmg_get_level_points, level_points, double)
+GMG_LEVEL_GETTER(gmg_get_all_triangles, all_triangles, int32_t)
+GMG_LEVEL_GETTER(gmg_get_notrimap, no_tri_found, int32_t)
+#undef GMG_LEVEL_GETTER
+
+// ---- solve ------------------------------------------------------------------------------
+int gmg_stage_system(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t* a_indices,
+                     const double* a_data, const double* rhs, int32_t K) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(a_indptr && a_indices && a_data && rhs, "null argument");
+        engine(h).stage_system(n, a_indptr, a_indices, a_data, rhs, K);
+    });
+}
+
+int gmg_solve_staged(gmg_handle h) {
+    if (!h) return 1;
+    return guarded(h, [&] { engine(h).solve_staged(); });
+}
+
+int gmg_fetch_solution(gmg_handle h, double* x_out) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(x_out != nullptr, "null argument");
+        engine(h).fetch_solution(x_out);
+    });
+}
+
+int gmg_solve(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t* a_indices, const double* a_data,
+              const double* rhs, double* x_out, int32_t K) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(a_indptr && a_indices && a_data && rhs && x_out, "null argument");
+        gmg::EngineBase& e = engine(h);
+        e.stage_system(n, a_indptr, a_indices, a_data, rhs, K);
+        e.solve_staged();
+        e.fetch_solution(x_out);
+    });
+}
+
+int gmg_residual(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t* a_indices, const double* a_data,
+                 const double* rhs, const double* x, int32_t K, int32_t type, double* out) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(a_indptr && a_indices && a_data && rhs && x && out, "null argument");
+        *out = engine(h).residual(n, a_indptr, a_indices, a_data, rhs, x, K, type);
+    });
+}
+
+// ---- timing -----------------------------------------------------------------------------
+int gmg_timing_keys(gmg_handle h, int32_t which, char* buf, int64_t buflen) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(buf && buflen > 0, "null argument");
+        const auto& m = which == 0 ? h->s.hier.timing : h->s.solver_timing;
+        std::string joined;
+        for (const auto& kv : m) {
+            if (!joined.empty()) joined += ',';
+            joined += kv.first;
+        }
+        require((int64_t)joined.size() + 1 <= buflen, "buffer too small");
+        std::memcpy(buf, joined.c_str(), joined.size() + 1);
+    });
+}
+
+int gmg_get_timing(gmg_handle h, int32_t which, const char* key, double* out) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(key && out, "null argument");
+        const auto& m = which == 0 ? h->s.hier.timing : h->s.solver_timing;
+        auto it = m.find(key);
+        require(it != m.end(), "unknown timing key");
+        *out = it->second;
+    });
+}
+
+int gmg_get_convergence(gmg_handle h, double* t_ms, double* residue, int32_t* count) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(count != nullptr, "null argument");
+        const auto& c = h->s.convergence;
+        if (t_ms && residue) {
+            require(*count >= (int)c.size(), "output buffer too small");
+            for (size_t i = 0; i < c.size(); ++i) t_ms[i] = c[i].first, residue[i] = c[i].second;
+        }
+        *count = (int32_t)c.size();
+    });
+}
+
+// ---- measurement ------------------------------------------------------------------------
+int gmg_level_info(gmg_handle h, int32_t level, int64_t* rows, int64_t* nnz_a, int64_t* nnz_u) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(rows && nnz_a && nnz_u, "null argument");
+        require(h->s.engine && h->s.engine->level_info(level, rows, nnz_a, nnz_u), "no such level staged on the device");
+    });
+}
+
+int gmg_kernel_profile(gmg_handle h, int32_t kind, int32_t level, double* total_ms, int64_t* launches) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(total_ms && launches, "null argument");
+        *total_ms = 0.0, *launches = 0;
+        if (h->s.engine) h->s.engine->kernel_profile(kind, level, total_ms, launches);
+    });
+}
+
+int gmg_reset_kernel_profile(gmg_handle h) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        if (h->s.engine) h->s.engine->reset_kernel_profile();
+    });
+}
+
+int gmg_last_launch_count(gmg_handle h, int64_t* launches) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(launches != nullptr, "null argument");
+        *launches = h->s.last_launches;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// Shared CUDA helpers: error checking, RAII device buffers, sm_100a async-copy primitives.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace gmg {
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+    if (e != cudaSuccess) {
+        char buf[512];
+        std::snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorName(e), file, line, what);
+        cudaGetLastError();  // clear the sticky-less error state
+        throw CudaError(buf);
+    }
+}
+#define GMG_CUDA(expr) ::gmg::cuda_check((expr), #expr, __FILE__, __LINE__)
+
+// Device allocation owned by the solver handle. Arrays read by bulk copies are allocated with
+// `pad` extra elements so a 16-byte aligned over-read at the tail stays inside the allocation.
+template <typename T>
+struct DeviceBuffer {
+    T* ptr = nullptr;
+    size_t count = 0;
+    DeviceBuffer() = default;
+    DeviceBuffer(const DeviceBuffer&) = delete;
+    DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+    DeviceBuffer(DeviceBuffer&& o) noexcept : ptr(o.ptr), count(o.count) { o.ptr = nullptr, o.count = 0; }
+    DeviceBuffer& operator=(DeviceBuffer&& o) noexcept {
+        if (this != &o) {
+            release();
+            ptr = o.ptr, count = o.count;
+            o.ptr = nullptr, o.count = 0;
+        }
+        return *this;
+    }
+    ~DeviceBuffer() { release(); }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        count = 0;
+    }
+    // Grow-only allocation; contents are not preserved.
+    void ensure(size_t n, size_t pad = 0) {
+        if (n + pad <= count && ptr) return;
+        release();
+        GMG_CUDA(cudaMalloc((void**)&ptr, (n + pad ? n + pad : 1) * sizeof(T)));
+        count = n + pad;
+    }
+    void zero(cudaStream_t s) { if (ptr) GMG_CUDA(cudaMemsetAsync(ptr, 0, count * sizeof(T), s)); }
+    void upload(const T* host, size_t n, cudaStream_t s, size_t pad = 0) {
+        ensure(n, pad);
+        if (n) GMG_CUDA(cudaMemcpyAsync(ptr, host, n * sizeof(T), cudaMemcpyHostToDevice, s));
+        if (pad) GMG_CUDA(cudaMemsetAsync(ptr + n, 0, pad * sizeof(T), s));
+    }
+    void upload(const std::vector<T>& host, cudaStream_t s, size_t pad = 0) { upload(host.data(), host.size(), s, pad); }
+};
+
+#ifdef __CUDACC__
+// ---- mbarrier + bulk asynchronous copy (TMA engine, SASS UBLKCP) ---------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(arrivals) : "memory");
+}
+// Make barrier initialisation visible to the async proxy before the first bulk copy targets it.
+__device__ __forceinline__ void mbar_init_fence() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// One arrival that also announces `bytes` of pending bulk-copy traffic for the current phase.
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy; dst, src and bytes must be multiples of 16.
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
+}  // namespace gmg

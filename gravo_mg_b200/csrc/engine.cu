@@ -1,0 +1,710 @@
+// Device engine: stages the operators once, recomputes the Galerkin chain and the coarse
+// factor per solve, and runs the V-cycle loop
+//     do { V-cycle; residualCheck } while (residue > tol && iter < max_iter)
+// (reference multigrid_solver.cpp:1367-1449, 1059-1088) as a fixed list of kernel launches
+// that is captured once into a CUDA graph and replayed per cycle — or wrapped in a device-side
+// while-node so the whole loop is one launch.
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+
+#include "dense_coarse.h"
+#include "solver.h"
+#include "sparse_kernels.h"
+
+namespace gmg {
+namespace {
+
+enum OpKind { OP_JACOBI = 0, OP_RESIDUAL = 1, OP_RESTRICT = 2, OP_PROLONG = 3, OP_NORM = 4, OP_COARSE = 5, OP_ZERO = 6, OP_KINDS = 7 };
+constexpr int kMaxLevels = 16;
+
+// CSR matrix on the device. Setup arithmetic (Galerkin products, factorisation) is always
+// fp64 (`v64`); when the smoother runs in fp32 a cast copy `v32` is what the cycle reads.
+template <typename T>
+struct DevMat {
+    int rows = 0, cols = 0;
+    int64_t nnz = 0;
+    DeviceBuffer<int> indptr, indices, rowidx, tiles;
+    DeviceBuffer<double> v64;
+    DeviceBuffer<float> v32;
+    SpmvPlan plan;
+
+    const T* vals() const;
+    void upload_pattern(const HostCsr& m, cudaStream_t s) {
+        rows = (int)m.rows, cols = (int)m.cols, nnz = m.nnz();
+        indptr.upload(m.indptr, s);
+        indices.upload(m.indices.data(), m.indices.size(), s, 8);
+        v64.ensure(nnz, 8);
+        GMG_CUDA(cudaMemsetAsync(v64.ptr, 0, (nnz + 8) * sizeof(double), s));
+        if (sizeof(T) == 4) {
+            v32.ensure(nnz, 8);
+            GMG_CUDA(cudaMemsetAsync(v32.ptr, 0, (nnz + 8) * sizeof(float), s));
+        }
+    }
+    void upload_values(const double* host, cudaStream_t s) {
+        if (nnz) GMG_CUDA(cudaMemcpyAsync(v64.ptr, host, nnz * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    void refresh_cast(cudaStream_t s) {
+        if (sizeof(T) == 4) launch_cast_f64_f32(v64.ptr, v32.ptr, (size_t)nnz, s);
+    }
+    void make_rowidx(cudaStream_t s) {
+        rowidx.ensure(std::max<int64_t>(nnz, 1));
+        launch_expand_rows(rows, indptr.ptr, rowidx.ptr, s);
+    }
+    // Choose the kernel path and build the row tiles for the staged one.
+    void make_plan(const std::vector<int>& indptr_h, int prefer_path, cudaStream_t s) {
+        const double avg = rows ? (double)nnz / rows : 0.0;
+        int lanes = 1;
+        while (lanes < 32 && lanes < avg) lanes *= 2;
+        plan = SpmvPlan();
+        plan.lanes = lanes;
+        plan.path = 1;
+        if (prefer_path == 0 && rows > 0) {
+            // stage budget: 3 stages, two resident CTAs per SM
+            const size_t per_stage = (staged_smem_limit() / 2 - 256) / kStagedStages;
+            const int cap = (int)(per_stage / (sizeof(T) + sizeof(int))) & ~3;
+            int worst = 0;
+            std::vector<int> t = plan_row_tiles(indptr_h, kStagedThreads, cap, &worst);
+            if (worst <= cap) {
+                tiles.upload(t, s);
+                plan.path = 0;
+                plan.n_tiles = (int)t.size() - 1;
+                plan.stage_elems = std::max((worst + 3) & ~3, 4);
+                plan.tile_rows = tiles.ptr;
+                GMG_CUDA(cudaStreamSynchronize(s));  // `t` is a local
+            }
+        }
+    }
+};
+template <> const double* DevMat<double>::vals() const { return v64.ptr; }
+template <> const float* DevMat<float>::vals() const { return v32.ptr; }
+
+struct ProfileSlot {
+    double ms = 0.0;
+    int64_t launches = 0;
+};
+
+template <typename T>
+class Engine : public EngineBase {
+public:
+    explicit Engine(SolverState* st) : st_(st) {
+        int count = 0;
+        GMG_CUDA(cudaGetDeviceCount(&count));
+        if (count <= 0) throw CudaError("no CUDA device available (this library has no CPU fallback)");
+        if (st->params.device < 0 || st->params.device >= count) throw std::invalid_argument("invalid CUDA device ordinal");
+        GMG_CUDA(cudaSetDevice(st->params.device));
+        GMG_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+        for (auto& e : ev_) GMG_CUDA(cudaEventCreate(&e));
+        ctl_.ensure(2);
+        GMG_CUDA(cudaMemsetAsync(ctl_.ptr, 0, 2 * sizeof(CycleControl), stream_));
+        partials_.ensure(kNormChunkStride * kMaxNormChunks);
+        GMG_CUDA(cudaMallocHost((void**)&ctl_host_, sizeof(CycleControl)));
+        std::vector<double> minv(st->mass_diag.size());
+        for (size_t i = 0; i < minv.size(); ++i) minv[i] = st->mass_diag[i] != 0.0 ? 1.0 / st->mass_diag[i] : 0.0;  // igl::invert_diag
+        mass_.upload(st->mass_diag, stream_);
+        minv_.upload(minv, stream_);
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+    }
+
+    ~Engine() override {
+        cudaSetDevice(st_->params.device);
+        drop_graphs();
+        for (auto& e : ev_) cudaEventDestroy(e);
+        for (auto& e : prof_events_) cudaEventDestroy(e);
+        if (ctl_host_) cudaFreeHost(ctl_host_);
+        if (stream_) cudaStreamDestroy(stream_);
+    }
+
+    void invalidate_hierarchy() override {
+        hierarchy_ready_ = false;
+        pattern_ready_ = false;
+        invalidate_cycle();
+    }
+    void invalidate_cycle() override {
+        cycle_dirty_ = true;
+    }
+
+    // ------------------------------------------------------------------ staging
+    void stage_system(int64_t n, const int* indptr, const int* indices, const double* data, const double* rhs,
+                      int K) override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        if (n != st_->n) throw std::invalid_argument("lhs has a different number of rows than the point set of the constructor");
+        if (K < 1 || K > kMaxRhsTile * kMaxNormChunks) throw std::invalid_argument("number of right-hand sides must be 1..32");
+        if (indptr[0] != 0) throw std::invalid_argument("lhs indptr must start at 0");
+        const int64_t nnz = indptr[n];
+        if (!hierarchy_ready_) upload_hierarchy();
+        const bool same = pattern_ready_ && (int64_t)a_indptr_h_.size() == n + 1 && (int64_t)a_indices_h_.size() == nnz &&
+                          std::memcmp(a_indptr_h_.data(), indptr, (n + 1) * sizeof(int)) == 0 &&
+                          std::memcmp(a_indices_h_.data(), indices, nnz * sizeof(int)) == 0;
+        if (!same) setup_pattern(n, indptr, indices);
+        lv_[0].A.upload_values(data, stream_);
+        if (K != K_) {
+            K_ = K;
+            allocate_vectors();
+            invalidate_cycle();
+        }
+        GMG_CUDA(cudaMemcpyAsync(rhs64_.ptr, rhs, (size_t)n * K * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+        staged_ = true;
+    }
+
+    void fetch_solution(double* x_out) override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        if (!solved_) throw std::logic_error("fetch_solution before solve_staged");
+        const size_t count = (size_t)st_->n * K_;
+        if (sizeof(T) == 4) launch_cast_f32_f64(reinterpret_cast<const float*>(x_final_), x64_.ptr, count, stream_);
+        const double* src = sizeof(T) == 4 ? x64_.ptr : reinterpret_cast<const double*>(x_final_);
+        GMG_CUDA(cudaMemcpyAsync(x_out, src, count * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+    }
+
+    // ------------------------------------------------------------------ solve
+    void solve_staged() override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        if (!staged_) throw std::logic_error("solve_staged before stage_system");
+        const gmg_params& p = st_->params;
+        if (p.cycle_type != 0) throw std::invalid_argument("only cycle_type 0 (V-cycle) is implemented on the device path");
+        if (p.max_iter < 1) throw std::invalid_argument("max_iter must be >= 1");
+        if (p.stopping_criteria < 0 || p.stopping_criteria > 3) throw std::invalid_argument("stopping_criteria must be 0..3");
+        const int L = n_levels_;
+        if (hist_res_.count < (size_t)p.max_iter) {
+            drop_graphs();  // captured launches hold the old history pointers
+            hist_res_.ensure(p.max_iter);
+            hist_ms_.ensure(p.max_iter);
+        }
+        if (cycle_dirty_) build_cycle();
+        int64_t launches = 0;
+
+        GMG_CUDA(cudaMemsetAsync(ctl_.ptr, 0, sizeof(CycleControl), stream_));
+        GMG_CUDA(cudaEventRecord(ev_[0], stream_));
+        // x0 = rhs (core.cpp:69), b = rhs
+        set_initial_guess();
+        launches += sizeof(T) == 4 ? 2 : 0;
+
+        // ---- "reduction": Abar[k+1] = U[k]^T Abar[k] U[k] (multigrid_solver.cpp:1387-1392)
+        launch_extract_dinv<T>(lv_[0].n, lv_[0].A.indptr.ptr, lv_[0].A.indices.ptr, lv_[0].A.v64.ptr, lv_[0].dinv.ptr, ctl_.ptr, stream_);
+        lv_[0].A.refresh_cast(stream_);
+        ++launches;
+        for (int k = 0; k < L; ++k) {
+            Level& f = lv_[k];
+            Level& c = lv_[k + 1];
+            launch_spgemm_numeric(f.AP.nnz, f.AP.rowidx.ptr, f.AP.indices.ptr, f.AP.v64.ptr, f.A.indptr.ptr, f.A.indices.ptr,
+                                  f.A.v64.ptr, f.P.indptr.ptr, f.P.indices.ptr, f.P.v64.ptr, stream_);
+            launch_spgemm_numeric(c.A.nnz, c.A.rowidx.ptr, c.A.indices.ptr, c.A.v64.ptr, f.R.indptr.ptr, f.R.indices.ptr,
+                                  f.R.v64.ptr, f.AP.indptr.ptr, f.AP.indices.ptr, f.AP.v64.ptr, stream_);
+            launches += 2;
+            if (k + 1 < L) {
+                launch_extract_dinv<T>(c.n, c.A.indptr.ptr, c.A.indices.ptr, c.A.v64.ptr, c.dinv.ptr, ctl_.ptr, stream_);
+                c.A.refresh_cast(stream_);
+                ++launches;
+            }
+        }
+        GMG_CUDA(cudaEventRecord(ev_[1], stream_));
+
+        // ---- "coarsest_solve": factor Abar[L] (multigrid_solver.cpp:1401)
+        coarse_.factor(lv_[L].A.indptr.ptr, lv_[L].A.indices.ptr, lv_[L].A.v64.ptr, ctl_.ptr, stream_);
+        launches += coarse_.launches_per_factor();
+        GMG_CUDA(cudaEventRecord(ev_[2], stream_));
+
+        // ---- "cycles" (multigrid_solver.cpp:1411-1417)
+        launch_cycle_begin(ctl_.ptr, p.max_iter, p.stopping_criteria, p.tolerance, K_, stream_);
+        ++launches;
+        const bool graph = st_->use_graph && !st_->profile;
+        if (graph && st_->loop_mode == 1) {
+            if (!while_exec_) build_while_graph();
+            GMG_CUDA(cudaGraphLaunch(while_exec_, stream_));
+        } else {
+            if (graph && !cycle_exec_) build_cycle_graph();
+            for (int it = 0; it < p.max_iter; ++it) {
+                if (graph)
+                    GMG_CUDA(cudaGraphLaunch(cycle_exec_, stream_));
+                else
+                    run_cycle(stream_, 0, st_->profile);
+                GMG_CUDA(cudaMemcpyAsync(ctl_host_, ctl_.ptr, sizeof(CycleControl), cudaMemcpyDeviceToHost, stream_));
+                GMG_CUDA(cudaStreamSynchronize(stream_));
+                if (ctl_host_->done || ctl_host_->error) break;
+            }
+        }
+        GMG_CUDA(cudaEventRecord(ev_[3], stream_));
+        GMG_CUDA(cudaMemcpyAsync(ctl_host_, ctl_.ptr, sizeof(CycleControl), cudaMemcpyDeviceToHost, stream_));
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+        if (st_->profile) collect_profile();
+
+        const int iters = ctl_host_->iter;
+        launches += (int64_t)iters * launches_per_cycle_;
+        st_->last_launches = launches;
+        std::vector<double> res(std::max(iters, 1)), ms(std::max(iters, 1));
+        if (iters > 0) {
+            GMG_CUDA(cudaMemcpy(res.data(), hist_res_.ptr, iters * sizeof(double), cudaMemcpyDeviceToHost));
+            GMG_CUDA(cudaMemcpy(ms.data(), hist_ms_.ptr, iters * sizeof(double), cudaMemcpyDeviceToHost));
+        }
+        st_->convergence.clear();
+        for (int i = 0; i < iters; ++i) st_->convergence.emplace_back(ms[i], res[i]);
+        float t01 = 0, t12 = 0, t23 = 0, t03 = 0;
+        GMG_CUDA(cudaEventElapsedTime(&t01, ev_[0], ev_[1]));
+        GMG_CUDA(cudaEventElapsedTime(&t12, ev_[1], ev_[2]));
+        GMG_CUDA(cudaEventElapsedTime(&t23, ev_[2], ev_[3]));
+        GMG_CUDA(cudaEventElapsedTime(&t03, ev_[0], ev_[3]));
+        auto& tm = st_->solver_timing;
+        tm["reduction"] = t01;
+        tm["coarsest_solve"] = t12;
+        tm["cycles"] = t23;
+        tm["solver_total"] = t03;
+        tm["iterations"] = (double)iters;
+        tm["residue"] = ctl_host_->residue;
+        solved_ = true;
+        if (ctl_host_->error & 1) throw std::runtime_error("an operator has a missing, non-positive or non-finite diagonal entry (Jacobi smoother needs A_ii > 0)");
+        if (ctl_host_->error & 4) throw std::runtime_error("coarsest-level Cholesky broke down: the Galerkin operator is not positive definite");
+        if (ctl_host_->error & 2) throw std::runtime_error("residual became non-finite (diverged); try a smaller omega");
+    }
+
+    // ------------------------------------------------------------------ residualCheck
+    double residual(int64_t n, const int* indptr, const int* indices, const double* data, const double* rhs,
+                    const double* x, int K, int type) override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        if (n != st_->n) throw std::invalid_argument("lhs has a different number of rows than the point set of the constructor");
+        if (type < 0 || type > 3) throw std::invalid_argument("residual type must be 0..3");
+        if (K < 1 || K > kMaxRhsTile * kMaxNormChunks) throw std::invalid_argument("number of right-hand sides must be 1..32");
+        const int64_t nnz = indptr[n];
+        q_indptr_.upload(indptr, n + 1, stream_);
+        q_indices_.upload(indices, nnz, stream_, 8);
+        q_vals_.upload(data, nnz, stream_, 8);
+        q_b_.upload(rhs, (size_t)n * K, stream_);
+        q_x_.upload(x, (size_t)n * K, stream_);
+        CycleControl* aux = ctl_.ptr + 1;
+        launch_cycle_begin(aux, 1, type, 0.0, K, stream_);
+        SpmvPlan plan;
+        plan.path = 1;
+        plan.lanes = 1;
+        SpmvArgs<double> a;
+        a.n_rows = (int)n, a.ld = K;
+        a.rowptr = q_indptr_.ptr, a.colidx = q_indices_.ptr, a.vals = q_vals_.ptr;
+        a.weight = type == 2 ? mass_.ptr : type == 1 ? minv_.ptr : nullptr;
+        NormChunks chunks;
+        for (int k0 = 0; k0 < K; k0 += kMaxRhsTile) {
+            const int kt = std::min(kMaxRhsTile, K - k0);
+            a.x = q_x_.ptr + k0, a.b = q_b_.ptr + k0;
+            a.partials = partials_.ptr + (size_t)chunks.n_chunks * kNormChunkStride;
+            chunks.kt[chunks.n_chunks] = kt;
+            chunks.n_blocks[chunks.n_chunks] = launch_spmv<double>(EPI_NORM, kt, a, plan, stream_);
+            ++chunks.n_chunks;
+        }
+        launch_norm_finalize(partials_.ptr, chunks, aux, nullptr, nullptr, 0, 0, stream_);
+        GMG_CUDA(cudaMemcpyAsync(ctl_host_, aux, sizeof(CycleControl), cudaMemcpyDeviceToHost, stream_));
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+        return ctl_host_->residue;
+    }
+
+    bool level_info(int level, int64_t* rows, int64_t* nnz_a, int64_t* nnz_u) override {
+        if (!pattern_ready_ || level < 0 || level > n_levels_) return false;
+        *rows = lv_[level].n;
+        *nnz_a = lv_[level].A.nnz;
+        *nnz_u = level < n_levels_ ? lv_[level].P.nnz : 0;
+        return true;
+    }
+    void kernel_profile(int kind, int level, double* total_ms, int64_t* launches) override {
+        *total_ms = 0.0, *launches = 0;
+        if (kind < 0 || kind >= OP_KINDS) return;
+        for (int l = 0; l < kMaxLevels; ++l) {
+            if (level >= 0 && l != level) continue;
+            *total_ms += prof_[kind][l].ms;
+            *launches += prof_[kind][l].launches;
+        }
+    }
+    void reset_kernel_profile() override {
+        for (auto& row : prof_)
+            for (auto& s : row) s = ProfileSlot();
+    }
+
+private:
+    struct Level {
+        int n = 0;
+        DevMat<T> A;    // operator of this level (level 0: the caller's lhs; k >= 1: Galerkin)
+        DevMat<T> P;    // U[k]    : n_k x n_{k+1}
+        DevMat<T> R;    // U[k]^T  : n_{k+1} x n_k, explicit so restriction is a gather
+        DevMat<T> AP;   // A_k U_k : intermediate of the Galerkin product (fp64 only)
+        DeviceBuffer<T> dinv, x, t, b, r;
+    };
+    struct Op {
+        int kind = 0, level = 0, epi = 0;
+        SpmvArgs<T> args;
+        const SpmvPlan* plan = nullptr;
+        void* zero_ptr = nullptr;
+        size_t zero_bytes = 0;
+    };
+
+    // ---- setup -------------------------------------------------------------------------
+    void upload_hierarchy() {
+        const auto& U = st_->hier.U;
+        n_levels_ = (int)U.size();
+        if (n_levels_ + 1 > kMaxLevels) throw std::invalid_argument("too many levels");
+        lv_.clear();
+        lv_.resize(n_levels_ + 1);
+        lv_[0].n = (int)st_->n;
+        r_host_.clear();
+        for (int k = 0; k < n_levels_; ++k) {
+            const HostCsr& u = U[k];
+            if (u.rows != lv_[k].n) throw std::invalid_argument("prolongation matrix has the wrong number of rows for its level");
+            lv_[k + 1].n = (int)u.cols;
+            lv_[k].P.upload_pattern(u, stream_);
+            lv_[k].P.upload_values(u.data.data(), stream_);
+            lv_[k].P.refresh_cast(stream_);
+            lv_[k].P.make_plan(u.indptr, st_->kernel_path, stream_);
+            HostCsr r = transpose(u);
+            lv_[k].R.upload_pattern(r, stream_);
+            lv_[k].R.upload_values(r.data.data(), stream_);
+            lv_[k].R.refresh_cast(stream_);
+            lv_[k].R.make_plan(r.indptr, st_->kernel_path, stream_);
+            r_host_.push_back(std::move(r));
+        }
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+        hierarchy_ready_ = true;
+        pattern_ready_ = false;
+    }
+
+    // Symbolic phase, once per sparsity pattern of the lhs: patterns of A_k U_k and of every
+    // Galerkin operator, their tile plans, and the coarse workspace.
+    void setup_pattern(int64_t n, const int* indptr, const int* indices) {
+        const int64_t nnz = indptr[n];
+        a_indptr_h_.assign(indptr, indptr + n + 1);
+        a_indices_h_.assign(indices, indices + nnz);
+        HostCsr cur;
+        cur.rows = cur.cols = n;
+        cur.indptr = a_indptr_h_;
+        cur.indices = a_indices_h_;
+        lv_[0].A.upload_pattern(cur, stream_);
+        lv_[0].A.make_plan(cur.indptr, st_->kernel_path, stream_);
+        for (int k = 0; k < n_levels_; ++k) {
+            HostCsr ap = spgemm_symbolic(cur, st_->hier.U[k]);
+            HostCsr ac = spgemm_symbolic(r_host_[k], ap);
+            lv_[k].AP.upload_pattern(ap, stream_);
+            lv_[k].AP.make_rowidx(stream_);
+            lv_[k + 1].A.upload_pattern(ac, stream_);
+            lv_[k + 1].A.make_rowidx(stream_);
+            lv_[k + 1].A.make_plan(ac.indptr, st_->kernel_path, stream_);
+            cur = std::move(ac);
+        }
+        for (int k = 0; k <= n_levels_; ++k) lv_[k].dinv.ensure(std::max(lv_[k].n, 1));
+        coarse_.setup(lv_[n_levels_].n, stream_);
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+        pattern_ready_ = true;
+        if (K_) allocate_vectors();
+        invalidate_cycle();
+    }
+
+    void allocate_vectors() {
+        for (int k = 0; k <= n_levels_; ++k) {
+            const size_t count = (size_t)std::max(lv_[k].n, 1) * K_;
+            lv_[k].x.ensure(count), lv_[k].t.ensure(count), lv_[k].b.ensure(count), lv_[k].r.ensure(count);
+        }
+        rhs64_.ensure((size_t)st_->n * K_);
+        if (sizeof(T) == 4) {
+            x64_.ensure((size_t)st_->n * K_);
+            const size_t nc = (size_t)lv_[n_levels_].n * K_;
+            coarse_b64_.ensure(nc), coarse_x64_.ensure(nc);
+        }
+    }
+
+    void set_initial_guess() {
+        const size_t count = (size_t)st_->n * K_;
+        if (sizeof(T) == 8) {
+            GMG_CUDA(cudaMemcpyAsync(lv_[0].b.ptr, rhs64_.ptr, count * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+            GMG_CUDA(cudaMemcpyAsync(lv_[0].x.ptr, rhs64_.ptr, count * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+        } else {
+            launch_cast_f64_f32(rhs64_.ptr, reinterpret_cast<float*>(lv_[0].b.ptr), count, stream_);
+            launch_cast_f64_f32(rhs64_.ptr, reinterpret_cast<float*>(lv_[0].x.ptr), count, stream_);
+        }
+    }
+
+    // ---- the V-cycle as a launch list ----------------------------------------------------
+    SpmvArgs<T> base_args(const DevMat<T>& m) const {
+        SpmvArgs<T> a;
+        a.n_rows = m.rows;
+        a.ld = K_;
+        a.rowptr = m.indptr.ptr, a.colidx = m.indices.ptr, a.vals = m.vals();
+        a.omega = (T)st_->params.omega;
+        a.ctl = ctl_.ptr;
+        return a;
+    }
+
+    void push_sweeps(int k, int count, T*& cur, T*& alt) {
+        for (int i = 0; i < count; ++i) {
+            Op op;
+            op.kind = OP_JACOBI, op.level = k, op.epi = EPI_JACOBI, op.plan = &lv_[k].A.plan;
+            op.args = base_args(lv_[k].A);
+            op.args.x = cur, op.args.b = lv_[k].b.ptr, op.args.dinv = lv_[k].dinv.ptr, op.args.out = alt;
+            ops_.push_back(op);
+            std::swap(cur, alt);
+        }
+    }
+
+    // multiGridVCycleGS (multigrid_solver.cpp:1059-1088) at level k. `cur` holds x_k on entry and
+    // on exit; `pre_done` sweeps were already applied by the caller (zero-guess shortcut).
+    void push_vcycle(int k, T*& cur, T*& alt, int pre_done) {
+        const gmg_params& p = st_->params;
+        const int L = n_levels_;
+        Level& f = lv_[k];
+        Level& c = lv_[k + 1];
+        push_sweeps(k, p.pre_iters - pre_done, cur, alt);
+        {   // res = b - A x
+            Op op;
+            op.kind = OP_RESIDUAL, op.level = k, op.epi = EPI_RESIDUAL, op.plan = &f.A.plan;
+            op.args = base_args(f.A);
+            op.args.x = cur, op.args.b = f.b.ptr, op.args.out = f.r.ptr;
+            ops_.push_back(op);
+        }
+        // resRest = U^T res ; eps = 0. With a zero guess the first Jacobi sweep on the next level
+        // is eps = omega D^-1 resRest, which the restriction writes as a by-product.
+        const bool next_is_coarsest = (k + 1 == L);
+        const int next_pre_done = (!next_is_coarsest && p.pre_iters >= 1) ? 1 : 0;
+        {
+            Op op;
+            op.kind = OP_RESTRICT, op.level = k, op.epi = EPI_SPMV, op.plan = &f.R.plan;
+            op.args = base_args(f.R);
+            op.args.x = f.r.ptr, op.args.out = c.b.ptr;
+            if (next_pre_done) op.args.out2 = c.x.ptr, op.args.dinv = c.dinv.ptr;
+            ops_.push_back(op);
+        }
+        T* ccur = c.x.ptr;
+        T* calt = c.t.ptr;
+        if (next_is_coarsest) {
+            Op op;
+            op.kind = OP_COARSE, op.level = k + 1;
+            ops_.push_back(op);
+        } else {
+            if (!next_pre_done) {
+                Op op;
+                op.kind = OP_ZERO, op.level = k + 1, op.zero_ptr = c.x.ptr, op.zero_bytes = (size_t)c.n * K_ * sizeof(T);
+                ops_.push_back(op);
+            }
+            push_vcycle(k + 1, ccur, calt, next_pre_done);
+        }
+        {   // x = x + U eps. On level 0 an odd sweep count is evened out by writing to the other
+            // buffer, so a cycle always ends in the buffer it started from (graph replay).
+            Op op;
+            op.kind = OP_PROLONG, op.level = k, op.epi = EPI_ADD, op.plan = &f.P.plan;
+            op.args = base_args(f.P);
+            op.args.x = ccur, op.args.xin = cur;
+            const bool flip = (k == 0) && ((p.pre_iters + p.post_iters) % 2 != 0);
+            op.args.out = flip ? alt : cur;
+            ops_.push_back(op);
+            if (flip) std::swap(cur, alt);
+        }
+        push_sweeps(k, p.post_iters, cur, alt);
+    }
+
+    void build_cycle() {
+        drop_graphs();
+        ops_.clear();
+        T* cur = lv_[0].x.ptr;
+        T* alt = lv_[0].t.ptr;
+        if (n_levels_ == 0) {
+            // no hierarchy could be built (N <= lower_bound): the reference is undefined here
+            // (SURVEY Appendix A.13); the whole system goes to the direct coarse solve.
+            Op op;
+            op.kind = OP_COARSE, op.level = 0;
+            ops_.push_back(op);
+        } else {
+            push_vcycle(0, cur, alt, 0);
+        }
+        x_final_ = cur;
+        {   // residualCheck(LHS, b, x, stoppingCriteria) (multigrid_solver.cpp:1413)
+            Op op;
+            op.kind = OP_NORM, op.level = 0, op.epi = EPI_NORM, op.plan = &lv_[0].A.plan;
+            op.args = base_args(lv_[0].A);
+            op.args.x = cur, op.args.b = lv_[0].b.ptr;
+            ops_.push_back(op);
+        }
+        cycle_dirty_ = false;
+        // one-time per-kernel attribute/occupancy calls must not land inside a stream capture
+        set_launch_dry_run(true);
+        try {
+            for (const Op& op : ops_)
+                if (op.plan) run_op(op, stream_, 0);
+        } catch (...) {
+            set_launch_dry_run(false);
+            throw;
+        }
+        set_launch_dry_run(false);
+    }
+
+    int run_op(const Op& op, cudaStream_t s, unsigned long long cond) {
+        int launches = 0;
+        const gmg_params& p = st_->params;
+        switch (op.kind) {
+            case OP_ZERO:
+                GMG_CUDA(cudaMemsetAsync(op.zero_ptr, 0, op.zero_bytes, s));
+                break;
+            case OP_COARSE: {
+                Level& c = lv_[op.level];
+                if (sizeof(T) == 8) {
+                    coarse_.solve(reinterpret_cast<const double*>(c.b.ptr), reinterpret_cast<double*>(c.x.ptr), K_, K_, ctl_.ptr, s);
+                } else {
+                    const size_t count = (size_t)c.n * K_;
+                    launch_cast_f32_f64(reinterpret_cast<const float*>(c.b.ptr), coarse_b64_.ptr, count, s);
+                    coarse_.solve(coarse_b64_.ptr, coarse_x64_.ptr, K_, K_, ctl_.ptr, s);
+                    launch_cast_f64_f32(coarse_x64_.ptr, reinterpret_cast<float*>(c.x.ptr), count, s);
+                    launches += 2;
+                }
+                launches += 2 * ((K_ + kMaxRhsTile - 1) / kMaxRhsTile);
+                break;
+            }
+            case OP_NORM: {
+                NormChunks chunks;
+                SpmvArgs<T> a = op.args;
+                a.weight = p.stopping_criteria == 2 ? mass_.ptr : p.stopping_criteria == 1 ? minv_.ptr : nullptr;
+                for (int k0 = 0; k0 < K_; k0 += kMaxRhsTile) {
+                    const int kt = std::min(kMaxRhsTile, K_ - k0);
+                    a.x = op.args.x + k0, a.b = op.args.b + k0;
+                    a.partials = partials_.ptr + (size_t)chunks.n_chunks * kNormChunkStride;
+                    chunks.kt[chunks.n_chunks] = kt;
+                    chunks.n_blocks[chunks.n_chunks] = launch_spmv<T>(EPI_NORM, kt, a, *op.plan, s);
+                    ++chunks.n_chunks;
+                    ++launches;
+                }
+                launch_norm_finalize(partials_.ptr, chunks, ctl_.ptr, hist_res_.ptr, hist_ms_.ptr, 1, cond, s);
+                ++launches;
+                break;
+            }
+            default: {
+                for (int k0 = 0; k0 < K_; k0 += kMaxRhsTile) {
+                    const int kt = std::min(kMaxRhsTile, K_ - k0);
+                    SpmvArgs<T> a = op.args;
+                    a.x = op.args.x + k0;
+                    if (a.b) a.b = op.args.b + k0;
+                    if (a.xin) a.xin = op.args.xin + k0;
+                    a.out = op.args.out + k0;
+                    if (a.out2) a.out2 = op.args.out2 + k0;
+                    launch_spmv<T>(op.epi, kt, a, *op.plan, s);
+                    ++launches;
+                }
+            }
+        }
+        return launches;
+    }
+
+    void run_cycle(cudaStream_t s, unsigned long long cond, bool profile) {
+        int launches = 0;
+        for (const Op& op : ops_) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            if (profile) {
+                a = next_prof_event(), b = next_prof_event();
+                GMG_CUDA(cudaEventRecord(a, s));
+            }
+            launches += run_op(op, s, cond);
+            if (profile) {
+                GMG_CUDA(cudaEventRecord(b, s));
+                prof_pending_.push_back({op.kind, op.level, a, b});
+            }
+        }
+        launches_per_cycle_ = launches;
+    }
+
+    void build_cycle_graph() {
+        cudaGraph_t g = nullptr;
+        GMG_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+        try {
+            run_cycle(stream_, 0, false);
+        } catch (...) {
+            cudaStreamEndCapture(stream_, &g);
+            if (g) cudaGraphDestroy(g);
+            throw;
+        }
+        GMG_CUDA(cudaStreamEndCapture(stream_, &g));
+        GMG_CUDA(cudaGraphInstantiate(&cycle_exec_, g, 0));
+        GMG_CUDA(cudaGraphDestroy(g));
+    }
+
+    // One graph = the whole do { V-cycle; residualCheck } while (...) loop: a conditional WHILE
+    // node whose body is the captured cycle; the finalize kernel of the stopping test sets the
+    // loop condition on the device, so the host launches once per solve.
+    void build_while_graph() {
+        cudaGraph_t g = nullptr;
+        GMG_CUDA(cudaGraphCreate(&g, 0));
+        cudaGraphConditionalHandle handle;
+        GMG_CUDA(cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+        np.conditional.handle = handle;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        GMG_CUDA(cudaGraphAddNode(&node, g, nullptr, 0, &np));
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        GMG_CUDA(cudaStreamBeginCaptureToGraph(stream_, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        cudaGraph_t captured = nullptr;
+        try {
+            run_cycle(stream_, (unsigned long long)handle, false);
+        } catch (...) {
+            cudaStreamEndCapture(stream_, &captured);
+            cudaGraphDestroy(g);
+            throw;
+        }
+        GMG_CUDA(cudaStreamEndCapture(stream_, &captured));
+        GMG_CUDA(cudaGraphInstantiate(&while_exec_, g, 0));
+        GMG_CUDA(cudaGraphDestroy(g));
+    }
+
+    void drop_graphs() {
+        if (cycle_exec_) cudaGraphExecDestroy(cycle_exec_);
+        if (while_exec_) cudaGraphExecDestroy(while_exec_);
+        cycle_exec_ = nullptr, while_exec_ = nullptr;
+    }
+
+    cudaEvent_t next_prof_event() {
+        if (prof_next_ == prof_events_.size()) {
+            cudaEvent_t e;
+            GMG_CUDA(cudaEventCreate(&e));
+            prof_events_.push_back(e);
+        }
+        return prof_events_[prof_next_++];
+    }
+    void collect_profile() {
+        for (const auto& pe : prof_pending_) {
+            float ms = 0;
+            GMG_CUDA(cudaEventElapsedTime(&ms, pe.a, pe.b));
+            ProfileSlot& slot = prof_[pe.kind][std::min(pe.level, kMaxLevels - 1)];
+            slot.ms += ms;
+            slot.launches += 1;
+        }
+        prof_pending_.clear();
+        prof_next_ = 0;
+    }
+
+    struct PendingEvent {
+        int kind, level;
+        cudaEvent_t a, b;
+    };
+
+    SolverState* st_;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev_[4] = {};
+    std::vector<Level> lv_;
+    int n_levels_ = 0;
+    int K_ = 0;
+    DenseCoarseSolver coarse_;
+    DeviceBuffer<CycleControl> ctl_;
+    CycleControl* ctl_host_ = nullptr;
+    DeviceBuffer<double> hist_res_, hist_ms_, partials_, mass_, minv_, rhs64_, x64_, coarse_b64_, coarse_x64_;
+    DeviceBuffer<int> q_indptr_, q_indices_;
+    DeviceBuffer<double> q_vals_, q_b_, q_x_;
+    std::vector<int> a_indptr_h_, a_indices_h_;
+    std::vector<HostCsr> r_host_;
+    bool hierarchy_ready_ = false, pattern_ready_ = false, staged_ = false, solved_ = false, cycle_dirty_ = true;
+    std::vector<Op> ops_;
+    T* x_final_ = nullptr;
+    int launches_per_cycle_ = 0;
+    cudaGraphExec_t cycle_exec_ = nullptr, while_exec_ = nullptr;
+    std::vector<cudaEvent_t> prof_events_;
+    size_t prof_next_ = 0;
+    std::vector<PendingEvent> prof_pending_;
+    ProfileSlot prof_[OP_KINDS][kMaxLevels];
+};
+
+}  // namespace
+
+std::unique_ptr<EngineBase> make_engine(SolverState* state) {
+    if (state->params.dtype == GMG_DTYPE_F32) return std::unique_ptr<EngineBase>(new Engine<float>(state));
+    return std::unique_ptr<EngineBase>(new Engine<double>(state));
+}
+
+}  // namespace gmg

@@ -1,0 +1,55 @@
+// Solver handle behind the C ABI: hierarchy (host), device-resident levels, the V-cycle as a
+// list of kernel launches replayed through a CUDA graph, and the reference's timing maps.
+// Mirrors the state of MGBS::MultigridSolver that solve() touches
+// (reference gravomg/include/gravomg/multigrid_solver.h:105-108, 131-134, 142-146, 157-159).
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/gravomg_b200.h"
+#include "hierarchy.h"
+#include "host_sparse.h"
+
+namespace gmg {
+
+class EngineBase {
+public:
+    virtual ~EngineBase() = default;
+    virtual void stage_system(int64_t n, const int* indptr, const int* indices, const double* data, const double* rhs,
+                              int K) = 0;
+    virtual void solve_staged() = 0;
+    virtual void fetch_solution(double* x_out) = 0;
+    virtual double residual(int64_t n, const int* indptr, const int* indices, const double* data, const double* rhs,
+                            const double* x, int K, int type) = 0;
+    virtual void invalidate_hierarchy() = 0;
+    virtual void invalidate_cycle() = 0;
+    virtual bool level_info(int level, int64_t* rows, int64_t* nnz_a, int64_t* nnz_u) = 0;
+    virtual void kernel_profile(int kind, int level, double* total_ms, int64_t* launches) = 0;
+    virtual void reset_kernel_profile() = 0;
+};
+
+struct SolverState {
+    gmg_params params;
+    int64_t n = 0;
+    std::vector<double> mass_diag;   // lumped mass (constructor argument)
+    Hierarchy hier;                  // U[k] and the debug arrays
+    bool use_graph = true;
+    int loop_mode = 0;               // 0 host loop (one sync per cycle), 1 device while-graph
+    int kernel_path = 0;             // 0 staged (TMA) where it fits, 1 direct everywhere
+    bool profile = false;
+    std::map<std::string, double> solver_timing;           // reference solverTiming keys
+    std::vector<std::pair<double, double>> convergence;    // (elapsed ms, residue) per cycle
+    int64_t last_launches = 0;
+    std::string error;
+    std::unique_ptr<EngineBase> engine;                    // created on first device use
+};
+
+std::unique_ptr<EngineBase> make_engine(SolverState* state);
+
+}  // namespace gmg
+
+struct gmg_solver {
+    gmg::SolverState s;
+};

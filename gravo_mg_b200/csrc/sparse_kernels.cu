@@ -1,0 +1,295 @@
+#include "sparse_kernels.h"
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace gmg {
+
+// ------------------------------------------------------------------ small device kernels
+__global__ void cycle_begin_kernel(CycleControl* ctl, int max_iter, int criterion, double tol, int n_cols) {
+    ctl->iter = 0;
+    ctl->done = 0;
+    ctl->max_iter = max_iter;
+    ctl->criterion = criterion;
+    ctl->tol = tol;
+    ctl->residue = 1.7976931348623157e308;
+    ctl->t_start_ns = global_timer_ns();
+    ctl->n_cols = n_cols;
+    // ctl->error is sticky across the phases of one solve; the host clears it when staging
+}
+
+__global__ void norm_finalize_kernel(const double* __restrict__ partials, NormChunks chunks, CycleControl* ctl,
+                                     double* hist_res, double* hist_ms, int record, unsigned long long cond_handle) {
+    if (record && ctl->done) {
+        if (cond_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, 0);
+        return;
+    }
+    __shared__ double sums[2 * kMaxRhsTile * kMaxNormChunks];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int n_sums = 0;
+    for (int c = 0; c < chunks.n_chunks; ++c) {
+        const int nv = 2 * chunks.kt[c];
+        const double* part = partials + (size_t)c * kNormChunkStride;
+        for (int j = warp; j < nv; j += blockDim.x / 32) {
+            double s = 0.0;
+            for (int blk = lane; blk < chunks.n_blocks[c]; blk += 32) s += part[(size_t)blk * nv + j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) sums[n_sums + j] = s;
+        }
+        n_sums += nv;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int K = n_sums / 2;
+        double residue = 0.0;
+        if (ctl->criterion == 3) {
+            double tot = 0.0;
+            for (int k = 0; k < K; ++k) tot += sums[2 * k];
+            residue = sqrt(tot);
+        } else {
+            for (int k = 0; k < K; ++k) {  // maxCoeff over the right-hand sides
+                const double rk = sqrt(sums[2 * k] / sums[2 * k + 1]);
+                if (k == 0 || rk > residue || rk != rk) residue = rk;
+            }
+        }
+        ctl->residue = residue;
+        if (residue != residue) ctl->error |= 2;
+        if (record) {
+            const int it = ctl->iter;
+            hist_res[it] = residue;
+            hist_ms[it] = (double)(global_timer_ns() - ctl->t_start_ns) * 1e-6;
+            ctl->iter = it + 1;
+            const int keep_going = (residue > ctl->tol) && (it + 1 < ctl->max_iter);
+            ctl->done = !keep_going;
+            if (cond_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, keep_going ? 1u : 0u);
+        }
+    }
+}
+
+template <typename T>
+__global__ void extract_dinv_kernel(int n, const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                    const double* __restrict__ vals, T* __restrict__ dinv, CycleControl* ctl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double d = 0.0;
+    for (int p = rowptr[i]; p < rowptr[i + 1]; ++p)
+        if (colidx[p] == i) d += vals[p];
+    if (!(d > 0.0) || d > 1.7976931348623157e308) {
+        atomicOr(&ctl->error, 1);
+        dinv[i] = T(0);
+    } else {
+        dinv[i] = (T)(1.0 / d);
+    }
+}
+
+__global__ void cast_f64_f32_kernel(const double* __restrict__ s, float* __restrict__ d, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = (float)s[i];
+}
+__global__ void cast_f32_f64_kernel(const float* __restrict__ s, double* __restrict__ d, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = (double)s[i];
+}
+
+__global__ void expand_rows_kernel(int n_rows, const int* __restrict__ rowptr, int* __restrict__ rowidx) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    for (int p = rowptr[r]; p < rowptr[r + 1]; ++p) rowidx[p] = r;
+}
+
+__global__ void spgemm_numeric_kernel(int64_t nnz_c, const int* __restrict__ c_rowidx, const int* __restrict__ c_col,
+                                      double* __restrict__ c_val, const int* __restrict__ a_ptr,
+                                      const int* __restrict__ a_col, const double* __restrict__ a_val,
+                                      const int* __restrict__ b_ptr, const int* __restrict__ b_col,
+                                      const double* __restrict__ b_val) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nnz_c) return;
+    const int i = c_rowidx[e];
+    const int j = c_col[e];
+    double s = 0.0;
+    for (int p = a_ptr[i]; p < a_ptr[i + 1]; ++p) {
+        const int k = a_col[p];
+        int lo = b_ptr[k];
+        const int end = b_ptr[k + 1];
+        int hi = end;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (b_col[mid] < j)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        if (lo < end && b_col[lo] == j) s += a_val[p] * b_val[lo];
+    }
+    c_val[e] = s;
+}
+
+__global__ void csr_to_dense_kernel(int n, const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                    const double* __restrict__ vals, double* __restrict__ dense, int lda) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    for (int p = rowptr[r]; p < rowptr[r + 1]; ++p) dense[(size_t)colidx[p] * lda + r] = vals[p];  // column-major
+}
+
+// ------------------------------------------------------------------ launchers
+size_t staged_smem_bytes(int stage_elems, size_t value_size) {
+    return 128 + (size_t)kStagedStages * stage_elems * (value_size + sizeof(int));
+}
+
+size_t staged_smem_limit() {
+    static size_t limit = 0;
+    if (!limit) {
+        int dev = 0, v = 0;
+        GMG_CUDA(cudaGetDevice(&dev));
+        GMG_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        limit = (size_t)v;
+    }
+    return limit;
+}
+
+namespace {
+
+thread_local bool g_dry_run = false;
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        GMG_CUDA(cudaGetDevice(&dev));
+        GMG_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    }
+    return n;
+}
+
+// CTAs per SM for (kernel, smem): queried once, also opts the kernel into large dynamic smem.
+int resident_blocks(const void* kernel, int threads, size_t smem) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, size_t>, int> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(kernel, smem);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    if (smem > 48 * 1024) GMG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem_limit()));
+    int nb = 0;
+    GMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem));
+    if (nb < 1) nb = 1;
+    cache[key] = nb;
+    return nb;
+}
+
+template <typename T, int K, int EPI>
+int launch_one(SpmvArgs<T>& a, const SpmvPlan& plan, cudaStream_t stream) {
+    int grid = 0;
+    if (plan.path == 0) {
+        a.tile_rows = plan.tile_rows;
+        a.n_tiles = plan.n_tiles;
+        a.stage_elems = plan.stage_elems;
+        const size_t smem = staged_smem_bytes(plan.stage_elems, sizeof(T));
+        auto kernel = spmv_staged_kernel<T, K, EPI>;
+        const int per_sm = resident_blocks((const void*)kernel, kStagedThreads, smem);
+        grid = std::min(std::max(plan.n_tiles, 1), per_sm * num_sms());
+        if (EPI == EPI_NORM) grid = std::min(grid, kMaxNormBlocks);
+        if (!g_dry_run) kernel<<<grid, kStagedThreads, smem, stream>>>(a);
+    } else {
+        const int rows_per_block = kDirectThreads / plan.lanes;
+        const int64_t want = ((int64_t)a.n_rows + rows_per_block - 1) / rows_per_block;
+        grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)num_sms() * 32);
+        if (EPI == EPI_NORM) grid = std::min(grid, kMaxNormBlocks);
+        if (g_dry_run) return grid;
+        switch (plan.lanes) {
+            case 1: spmv_direct_kernel<T, K, EPI, 1><<<grid, kDirectThreads, 0, stream>>>(a); break;
+            case 2: spmv_direct_kernel<T, K, EPI, 2><<<grid, kDirectThreads, 0, stream>>>(a); break;
+            case 4: spmv_direct_kernel<T, K, EPI, 4><<<grid, kDirectThreads, 0, stream>>>(a); break;
+            case 8: spmv_direct_kernel<T, K, EPI, 8><<<grid, kDirectThreads, 0, stream>>>(a); break;
+            case 16: spmv_direct_kernel<T, K, EPI, 16><<<grid, kDirectThreads, 0, stream>>>(a); break;
+            default: spmv_direct_kernel<T, K, EPI, 32><<<grid, kDirectThreads, 0, stream>>>(a); break;
+        }
+    }
+    GMG_CUDA(cudaGetLastError());
+    return grid;
+}
+
+template <typename T, int K>
+int launch_k(int epi, SpmvArgs<T>& a, const SpmvPlan& plan, cudaStream_t stream) {
+    switch (epi) {
+        case EPI_SPMV: return launch_one<T, K, EPI_SPMV>(a, plan, stream);
+        case EPI_JACOBI: return launch_one<T, K, EPI_JACOBI>(a, plan, stream);
+        case EPI_RESIDUAL: return launch_one<T, K, EPI_RESIDUAL>(a, plan, stream);
+        case EPI_ADD: return launch_one<T, K, EPI_ADD>(a, plan, stream);
+        case EPI_NORM: return launch_one<T, K, EPI_NORM>(a, plan, stream);
+    }
+    throw std::invalid_argument("unknown epilogue");
+}
+
+}  // namespace
+
+void set_launch_dry_run(bool on) { g_dry_run = on; }
+
+template <typename T>
+int launch_spmv(int epi, int K, SpmvArgs<T> args, const SpmvPlan& plan, cudaStream_t stream) {
+    switch (K) {
+        case 1: return launch_k<T, 1>(epi, args, plan, stream);
+        case 2: return launch_k<T, 2>(epi, args, plan, stream);
+        case 3: return launch_k<T, 3>(epi, args, plan, stream);
+        case 4: return launch_k<T, 4>(epi, args, plan, stream);
+    }
+    throw std::invalid_argument("launch_spmv: K must be 1..4");
+}
+template int launch_spmv<double>(int, int, SpmvArgs<double>, const SpmvPlan&, cudaStream_t);
+template int launch_spmv<float>(int, int, SpmvArgs<float>, const SpmvPlan&, cudaStream_t);
+
+void launch_norm_finalize(const double* partials, const NormChunks& chunks, CycleControl* ctl, double* hist_res,
+                          double* hist_ms, int record, unsigned long long cond_handle, cudaStream_t stream) {
+    norm_finalize_kernel<<<1, 256, 0, stream>>>(partials, chunks, ctl, hist_res, hist_ms, record, cond_handle);
+    GMG_CUDA(cudaGetLastError());
+}
+
+void launch_cycle_begin(CycleControl* ctl, int max_iter, int criterion, double tol, int n_cols, cudaStream_t stream) {
+    cycle_begin_kernel<<<1, 1, 0, stream>>>(ctl, max_iter, criterion, tol, n_cols);
+    GMG_CUDA(cudaGetLastError());
+}
+
+template <typename T>
+void launch_extract_dinv(int n, const int* rowptr, const int* colidx, const double* vals, T* dinv, CycleControl* ctl,
+                         cudaStream_t stream) {
+    if (n <= 0) return;
+    extract_dinv_kernel<T><<<(n + 255) / 256, 256, 0, stream>>>(n, rowptr, colidx, vals, dinv, ctl);
+    GMG_CUDA(cudaGetLastError());
+}
+template void launch_extract_dinv<double>(int, const int*, const int*, const double*, double*, CycleControl*, cudaStream_t);
+template void launch_extract_dinv<float>(int, const int*, const int*, const double*, float*, CycleControl*, cudaStream_t);
+
+static int stream_grid(size_t n) { return (int)std::min<size_t>((n + 255) / 256, (size_t)148 * 16); }
+
+void launch_cast_f64_f32(const double* src, float* dst, size_t n, cudaStream_t stream) {
+    if (!n) return;
+    cast_f64_f32_kernel<<<stream_grid(n), 256, 0, stream>>>(src, dst, n);
+    GMG_CUDA(cudaGetLastError());
+}
+void launch_cast_f32_f64(const float* src, double* dst, size_t n, cudaStream_t stream) {
+    if (!n) return;
+    cast_f32_f64_kernel<<<stream_grid(n), 256, 0, stream>>>(src, dst, n);
+    GMG_CUDA(cudaGetLastError());
+}
+void launch_expand_rows(int n_rows, const int* rowptr, int* rowidx, cudaStream_t stream) {
+    if (n_rows <= 0) return;
+    expand_rows_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(n_rows, rowptr, rowidx);
+    GMG_CUDA(cudaGetLastError());
+}
+void launch_spgemm_numeric(int64_t nnz_c, const int* c_rowidx, const int* c_col, double* c_val, const int* a_ptr,
+                           const int* a_col, const double* a_val, const int* b_ptr, const int* b_col,
+                           const double* b_val, cudaStream_t stream) {
+    if (nnz_c <= 0) return;
+    const int64_t blocks = (nnz_c + 255) / 256;
+    spgemm_numeric_kernel<<<(unsigned)blocks, 256, 0, stream>>>(nnz_c, c_rowidx, c_col, c_val, a_ptr, a_col, a_val, b_ptr,
+                                                                b_col, b_val);
+    GMG_CUDA(cudaGetLastError());
+}
+void launch_csr_to_dense(int n, const int* rowptr, const int* colidx, const double* vals, double* dense, int lda,
+                         cudaStream_t stream) {
+    if (n <= 0) return;
+    csr_to_dense_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, rowptr, colidx, vals, dense, lda);
+    GMG_CUDA(cudaGetLastError());
+}
+
+}  // namespace gmg

@@ -1,0 +1,60 @@
+// Host-callable launchers for the sparse kernels (definitions in sparse_kernels.cu).
+#pragma once
+#include "sparse_kernels.cuh"
+
+namespace gmg {
+
+// How one CSR matrix is walked by the staged kernel; built once per sparsity pattern.
+struct SpmvPlan {
+    int path = 1;            // 0 staged (TMA), 1 direct
+    int lanes = 8;           // direct: threads per row (1, 2, 4, 8, 16, 32)
+    int n_tiles = 0;         // staged
+    int stage_elems = 0;     // staged: entries per stage (multiple of 4)
+    const int* tile_rows = nullptr;  // device array n_tiles + 1
+};
+
+constexpr int kMaxRhsTile = 4;        // kernels are instantiated for K = 1..4 columns per pass
+constexpr int kMaxNormBlocks = 148 * 16;
+constexpr int kMaxNormChunks = 8;     // => at most 32 right-hand sides per solve
+constexpr size_t kNormChunkStride = (size_t)kMaxNormBlocks * 2 * kMaxRhsTile;
+
+// NORM partial sums of a multi-pass (K > 4) residual: one (grid x 2*kt) block per pass.
+struct NormChunks {
+    int n_chunks = 0;
+    int kt[kMaxNormChunks] = {0};
+    int n_blocks[kMaxNormChunks] = {0};
+};
+
+size_t staged_smem_bytes(int stage_elems, size_t value_size);
+size_t staged_smem_limit();  // usable dynamic shared memory per CTA on this device
+
+// Launch acc = A x with epilogue `epi` over K (1..4) columns. Returns the grid size used
+// (NORM callers need it to finalize the partial sums).
+template <typename T>
+int launch_spmv(int epi, int K, SpmvArgs<T> args, const SpmvPlan& plan, cudaStream_t stream);
+
+// While on, launch_spmv does everything except launch (occupancy query, opt-in to large shared
+// memory): lets the one-time attribute calls happen outside of stream capture.
+void set_launch_dry_run(bool on);
+
+// Reduce NORM partials and update the loop state: residue, history, iter, done.
+// `cond_handle` != 0 additionally drives a CUDA graph while-node (cudaGraphSetConditional).
+void launch_norm_finalize(const double* partials, const NormChunks& chunks, CycleControl* ctl, double* hist_res,
+                          double* hist_ms, int record, unsigned long long cond_handle, cudaStream_t stream);
+void launch_cycle_begin(CycleControl* ctl, int max_iter, int criterion, double tol, int n_cols, cudaStream_t stream);
+
+template <typename T>
+void launch_extract_dinv(int n, const int* rowptr, const int* colidx, const double* vals, T* dinv, CycleControl* ctl,
+                         cudaStream_t stream);
+void launch_cast_f64_f32(const double* src, float* dst, size_t n, cudaStream_t stream);
+void launch_cast_f32_f64(const float* src, double* dst, size_t n, cudaStream_t stream);
+void launch_expand_rows(int n_rows, const int* rowptr, int* rowidx, cudaStream_t stream);
+// C = A * B on an existing sorted pattern of C, one thread per stored entry of C, products
+// added in the order of A's row (the order a row-wise CPU Gustavson pass uses).
+void launch_spgemm_numeric(int64_t nnz_c, const int* c_rowidx, const int* c_col, double* c_val, const int* a_ptr,
+                           const int* a_col, const double* a_val, const int* b_ptr, const int* b_col,
+                           const double* b_val, cudaStream_t stream);
+void launch_csr_to_dense(int n, const int* rowptr, const int* colidx, const double* vals, double* dense, int lda,
+                         cudaStream_t stream);
+
+}  // namespace gmg

@@ -1,0 +1,139 @@
+/* gravomg_b200 — C ABI of the B200-native Gravo MG V-cycle path.
+ *
+ * This is the drop-in boundary for ONE path of rubenwiersma/gravo_mg: what the pybind11
+ * module `gravomg_bindings` (reference gravomg_bindings/src/cpp/core.cpp:13-139) exposes
+ * around MGBS::MultigridSolver::solve (reference gravomg/src/multigrid_solver.cpp:1279-1485,
+ * solverType == 2). Host pointers in, host pointers out, plain sizes; device residency
+ * (operators, prolongations, Galerkin levels, CUDA graphs) is private to the handle.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; gmg_last_error(h) then
+ *     holds a message (h may be NULL for failures of gmg_create).
+ *   - sparse matrices are CSR with int32 indices and fp64 values.
+ *   - dense (N x K) blocks are row-major (numpy C order), fp64.
+ *   - there is no CPU fallback: anything that computes needs a CUDA device and fails
+ *     loudly without one. Hierarchy construction and the getters are host-only.
+ */
+#ifndef GRAVOMG_B200_H
+#define GRAVOMG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gmg_solver* gmg_handle;
+
+/* Enumerations of the reference (gravomg/include/gravomg/multigrid_solver.h:35-52). */
+enum { GMG_SAMPLING_FASTDISK = 0, GMG_SAMPLING_POISSONDISK = 1, GMG_SAMPLING_FPS = 2, GMG_SAMPLING_RANDOM = 3, GMG_SAMPLING_MIS = 4 };
+enum { GMG_WEIGHTING_BARYCENTRIC = 0, GMG_WEIGHTING_UNIFORM = 1, GMG_WEIGHTING_INVDIST = 2 };
+enum { GMG_SMOOTHER_JACOBI = 0 };
+enum { GMG_DTYPE_F64 = 0, GMG_DTYPE_F32 = 1 };
+
+/* Constructor arguments of the reference binding (core.cpp:20-58; Python defaults core.py:8-13)
+ * followed by the options this implementation adds. */
+typedef struct gmg_params {
+    double ratio;               /* 8.0   */
+    int32_t low_bound;          /* 1000  */
+    int32_t cycle_type;         /* 0 = V-cycle (only 0 is on the accelerated path) */
+    double tolerance;           /* 1e-4  */
+    int32_t stopping_criteria;  /* 2 = M-norm relative residual (multigrid_solver.cpp:1228-1277) */
+    int32_t pre_iters;          /* 2 */
+    int32_t post_iters;         /* 2 */
+    int32_t max_iter;           /* 100 */
+    int32_t check_voronoi;      /* 1 */
+    int32_t nested;             /* 0 */
+    int32_t sampling_strategy;  /* GMG_SAMPLING_FASTDISK (only one implemented) */
+    int32_t weighting;          /* GMG_WEIGHTING_BARYCENTRIC */
+    int32_t sig06;              /* must be 0 */
+    int32_t verbose;
+    int32_t debug;
+    int32_t ablation;           /* must be 0 */
+    int32_t ablation_num_points;
+    int32_t ablation_random;
+    /* ---- additions ---- */
+    int32_t smoother;           /* GMG_SMOOTHER_JACOBI: damped Jacobi x += omega D^-1 (b - A x) */
+    double omega;               /* damping, default 2/3 */
+    int32_t dtype;              /* GMG_DTYPE_F64 (default) | GMG_DTYPE_F32 smoother levels */
+    int32_t device;             /* CUDA device ordinal, default 0 */
+    int32_t build_hierarchy;    /* 1: build U at create (reference behaviour); 0: caller injects U */
+} gmg_params;
+
+/* Fill *p with the reference's Python defaults. */
+int gmg_default_params(gmg_params* p);
+
+/* Replaces the binding constructor core.cpp:20-58 (hierarchy built eagerly, core.cpp:49).
+ * pos: n x 3 row-major; neigh: n x kn row-major int32 padded with -1; mass: n x n CSR
+ * (must be diagonal: the lumped mass every reference caller passes). Host-only: no CUDA call. */
+int gmg_create(const gmg_params* p, int64_t n, const double* pos, const int32_t* neigh, int32_t kn,
+               const int32_t* m_indptr, const int32_t* m_indices, const double* m_data, gmg_handle* out);
+
+void gmg_destroy(gmg_handle h);
+const char* gmg_last_error(gmg_handle h);
+
+/* Change a solve-time setting after construction (the reference exposes them as public
+ * members: accuracy, stoppingCriteria, preIters, postIters, maxIter; multigrid_solver.h:131-144).
+ * Keys: "tolerance", "stopping_criteria", "pre_iters", "post_iters", "max_iter", "omega",
+ * and implementation knobs "use_graph" (0/1), "loop_mode" (0 host loop, 1 device while-graph),
+ * "kernel_path" (0 staged TMA, 1 direct), "profile" (0/1 per-kernel event timing). */
+int gmg_set_option(gmg_handle h, const char* key, double value);
+int gmg_get_option(gmg_handle h, const char* key, double* value);
+
+/* ---- hierarchy access: prolongation_matrices / set_prolongation_matrices (core.cpp:82-88) ---- */
+int gmg_num_levels(gmg_handle h, int32_t* n_prolongations);
+int gmg_prolongation_shape(gmg_handle h, int32_t level, int64_t* rows, int64_t* cols, int64_t* nnz);
+int gmg_get_prolongation(gmg_handle h, int32_t level, int32_t* indptr, int32_t* indices, double* data);
+/* Drop all prolongations, then set them one level at a time (level must equal the current count). */
+int gmg_clear_prolongations(gmg_handle h);
+int gmg_set_prolongation(gmg_handle h, int32_t level, int64_t rows, int64_t cols, const int32_t* indptr,
+                         const int32_t* indices, const double* data);
+
+/* sampling_indices / nearest_source / level_points (core.cpp:90-116). Query sizes with out == NULL. */
+int gmg_get_samples(gmg_handle h, int32_t level, int32_t* out, int64_t* count);
+int gmg_get_nearest_source(gmg_handle h, int32_t level, int32_t* out, int64_t* count);
+int gmg_get_level_points(gmg_handle h, int32_t level, double* out, int64_t* count);   /* debug=1 only */
+int gmg_get_all_triangles(gmg_handle h, int32_t level, int32_t* out, int64_t* count); /* debug=1 only */
+int gmg_get_notrimap(gmg_handle h, int32_t level, int32_t* out, int64_t* count);      /* debug=1 only */
+
+/* ---- the hot path: solve (core.cpp:68-72 -> multigrid_solver.cpp:1367-1449) ----
+ * x0 = rhs (core.cpp:69); Galerkin operators and the coarse factor are recomputed from the
+ * values of A on every call (multigrid_solver.cpp:1387-1401); at least one V-cycle runs; stops
+ * when residual(stopping_criteria) <= tolerance or after max_iter cycles. rhs, x_out: n x K. */
+int gmg_solve(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t* a_indices, const double* a_data,
+              const double* rhs, double* x_out, int32_t K);
+
+/* The same call split in three so a caller can keep the system resident in HBM:
+ * stage = host->device copies (+ symbolic setup when the sparsity pattern changed);
+ * solve_staged = reduction + coarse factor + cycles, device only; fetch = device->host. */
+int gmg_stage_system(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t* a_indices,
+                     const double* a_data, const double* rhs, int32_t K);
+int gmg_solve_staged(gmg_handle h);
+int gmg_fetch_solution(gmg_handle h, double* x_out);
+
+/* residualCheck (core.cpp:132-134 -> multigrid_solver.cpp:1228-1277). type 0..3. */
+int gmg_residual(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t* a_indices, const double* a_data,
+                 const double* rhs, const double* x, int32_t K, int32_t type, double* out);
+
+/* ---- timing maps and convergence trace (multigrid_solver.h:157-159; core.cpp:118-128) ----
+ * which: 0 = hierarchyTiming, 1 = solverTiming. Keys come back comma separated, in the
+ * alphabetical order std::map gives the reference's CSV writer (utility.cpp:106-131). */
+int gmg_timing_keys(gmg_handle h, int32_t which, char* buf, int64_t buflen);
+int gmg_get_timing(gmg_handle h, int32_t which, const char* key, double* out);
+/* capacity in *count on entry, number of cycles recorded on exit. */
+int gmg_get_convergence(gmg_handle h, double* t_ms, double* residue, int32_t* count);
+
+/* ---- measurement support (not part of the reference surface) ----
+ * Level sizes of the operators staged on the device: rows and stored entries of A_k, and of U_k. */
+int gmg_level_info(gmg_handle h, int32_t level, int64_t* rows, int64_t* nnz_a, int64_t* nnz_u);
+/* Per-kernel device time accumulated while option "profile" = 1. Kernel kinds:
+ * 0 jacobi, 1 residual, 2 restrict, 3 prolong_add, 4 norm, 5 coarse_solve. Level -1 sums levels. */
+int gmg_kernel_profile(gmg_handle h, int32_t kind, int32_t level, double* total_ms, int64_t* launches);
+int gmg_reset_kernel_profile(gmg_handle h);
+/* Number of kernel launches issued (or replayed through graphs) by the last solve. */
+int gmg_last_launch_count(gmg_handle h, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAVOMG_B200_H */
