@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the V-cycle hot path (BASELINE.json: V-cycles/sec and time-to-1e-6 residual on a
+1M-vertex Poisson system; fine-level smoother GB/s against the HBM peak).
+
+Workload at N=1 (BASELINE config 2): 1000 x 1000 torus grid (1 000 000 vertices, 7 000 000
+stored entries), lhs = 1e-6 M + S, rhs = M N(0,1) seed 42, fp64, K = 1, 5-level V-cycle
+(lower_bound 500), 2 pre + 2 post damped-Jacobi sweeps, stop at M-norm relative residual 1e-6.
+
+A step is one pass of the hot path: MultigridSolver::solve on the staged system — Galerkin
+reduction, coarse factorisation and V-cycles until the tolerance (multigrid_solver.cpp:1367-1449).
+  value      V-cycles/s over whole steps, operators resident in HBM (device time, CUDA events
+             recorded by the library on its own launch stream, max over ranks)
+  e2e        the same through gravomg.MultigridSolver.solve(lhs, rhs) with host arrays:
+             host->device copies of the matrix values and rhs and the device->host copy of x
+             are inside the timed region
+  roofline   fine-level Jacobi sweep: algorithmic bytes nnz*12 + n*36 over its mean launch
+             duration inside real V-cycles (per-launch CUDA events, profile pass of the same steps)
+  cpu_baseline  the CPU oracle (restated reference algorithm, lexicographic Gauss-Seidel, 1 thread
+             like the reference) on the same system on this box's host cores
+
+`--impl reference` times that CPU path alone and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "V-cycles/sec, 1M-vertex torus Poisson solve to 1e-6 M-norm residual"
+UNIT = "V-cycles/s"
+
+
+def build_problem(n_side):
+    from gravo_mg_b200 import synth
+
+    V, F = synth.torus_grid(n_side, n_side)
+    V, S, M, neigh = synth.mesh_operators(V, F)
+    lhs, rhs = synth.poisson_system(S, M)
+    return V, neigh, M, lhs, rhs
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])), mx.append(float(parts[2])), power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_run(V, neigh, M, lhs, rhs, U, tol, steps, warmup, budget_s=150.0):
+    """The reference algorithm on the host: oracle with lexicographic Gauss-Seidel, one thread
+    (the reference pins itself to one OpenMP thread, multigrid_solver.cpp:86-87)."""
+    from oracle import oracle
+
+    o = oracle.OracleSolver(M, U, tolerance=tol, smoother="gs", max_iter=100)
+    t0 = time.perf_counter()
+    o.solve(lhs, rhs)
+    first = time.perf_counter() - t0
+    t_first = dict(o.solver_timing)
+    total = steps + warmup
+    sample = "full solve to tolerance per step"
+    max_iter = 100
+    if first * (total - 1) > budget_s and total > 1:
+        per_cycle = t_first["cycles"] / t_first["iterations"] / 1e3
+        fixed = (t_first["reduction"] + t_first["coarsest_solve"]) / 1e3
+        max_iter = max(1, int((budget_s / (total - 1) - fixed) / per_cycle))
+        max_iter = min(max_iter, int(t_first["iterations"]))
+        sample = f"first {max_iter} V-cycles of the solve per step (bounded sample; full solve takes {int(t_first['iterations'])})"
+        o = oracle.OracleSolver(M, U, tolerance=tol, smoother="gs", max_iter=max_iter)
+    times, cycles, cyc_ms = [], [], []
+    runs = [(first, t_first)] if max_iter == 100 else []
+    while len(runs) < total:
+        t0 = time.perf_counter()
+        o.solve(lhs, rhs)
+        runs.append((time.perf_counter() - t0, dict(o.solver_timing)))
+    for dt, t in runs[warmup:]:
+        times.append(t["solver_total"] / 1e3)
+        cycles.append(t["iterations"])
+        cyc_ms.append(t["cycles"])
+    value = sum(cycles) / sum(times)
+    return {
+        "value": value, "ms_per_step": 1e3 * sum(times) / len(times), "sample": sample,
+        "cycles_per_step": sum(cycles) / len(cycles), "residue": runs[-1][1]["residue"],
+        "cycles_only_value": sum(cycles) / (sum(cyc_ms) / 1e3),
+        "full_solve_s": t_first["solver_total"] / 1e3, "full_solve_cycles": int(t_first["iterations"]),
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-side", type=int, default=1000)
+    ap.add_argument("--tol", type=float, default=1e-6)
+    ap.add_argument("--lower-bound", type=int, default=500)
+    ap.add_argument("--omega", type=float, default=2.0 / 3.0)
+    ap.add_argument("--loop-mode", type=int, default=1)
+    ap.add_argument("--kernel-path", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_side = args.n_side
+    workload = (f"torus {n_side}x{n_side} ({n_side * n_side} vertices) Poisson lhs=1e-6*M+S, fp64, K=1, "
+                f"V-cycle 2+2 sweeps, lower_bound={args.lower_bound}, tol={args.tol:g} (criterion 2, M-norm)")
+    config = {"workload": workload, "config_index": 1, "levels": None,
+              "l2": "operators + vectors of one solve (~250 MB at 1M vertices) exceed the 126 MB L2; a 512 MB buffer is also written between timed steps",
+              "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one system per GPU, no collective)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import gravomg
+
+        V, neigh, M, lhs, rhs = build_problem(n_side)
+        solver = gravomg.MultigridSolver(V, neigh, M, lower_bound=args.lower_bound)  # host-only: hierarchy
+        U = solver.prolongation_matrices
+        config["levels"] = [int(lhs.shape[0])] + [int(u.shape[1]) for u in U]
+        r = cpu_reference_run(V, neigh, M, lhs, rhs, U, args.tol, args.steps, args.warmup)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": 1, "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "smoother": "lexicographic Gauss-Seidel (reference algorithm)", "cycles_per_step": r["cycles_per_step"],
+            "cycles_only_vcycles_per_s": r["cycles_only_value"], "time_to_tol_s": r["full_solve_s"],
+            "cycles_to_tol": r["full_solve_cycles"], "residue": r["residue"],
+            "note": "reference cannot be built offline (needs libigl+Eigen); this is the CPU oracle port, single thread like the reference",
+        }
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+
+    import gravomg
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    V, neigh, M, lhs, rhs = build_problem(n_side)
+    n = lhs.shape[0]
+    solver = gravomg.MultigridSolver(V, neigh, M, lower_bound=args.lower_bound, tolerance=args.tol, max_iter=100,
+                                     omega=args.omega, device=local_rank)
+    b = solver.solver
+    b.set_option("loop_mode", args.loop_mode)
+    b.set_option("kernel_path", args.kernel_path)
+    U = solver.prolongation_matrices
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident steps
+    b.stage(lhs, rhs)
+    for _ in range(args.warmup):
+        b.solve_staged()
+    info = b.level_info()
+    config["levels"] = [lv["rows"] for lv in info]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
+    dev_ms, cyc_ms, cycles, launches = 0.0, 0.0, 0, 0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        b.solve_staged()  # synchronous; device time from the library's CUDA events
+        t = b.solver_timing()
+        dev_ms += t["solver_total"]
+        cyc_ms += t["cycles"]
+        cycles += int(t["iterations"])
+        launches += b.last_launch_count()
+    barrier()
+    wall = time.perf_counter() - wall0
+    residue = b.solver_timing()["residue"]
+    split = {k: b.solver_timing()[k] for k in ("reduction", "coarsest_solve", "cycles")}
+    dev_ms_max = max_over_ranks(dev_ms)
+    total_cycles = sum_over_ranks(cycles)
+    value = total_cycles / (dev_ms_max / 1e3)
+
+    # ---- end to end through the public API, host arrays in, host array out
+    x = solver.solve(lhs, rhs)
+    barrier()
+    e2e_t0 = time.perf_counter()
+    e2e_cycles = 0
+    for _ in range(args.steps):
+        x = solver.solve(lhs, rhs)
+        e2e_cycles += int(solver.solver_timing["iterations"])
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - e2e_t0)
+    clocks = sampler.stop()
+    e2e_value = sum_over_ranks(e2e_cycles) / e2e_s
+    h2d = lhs.indptr.nbytes // (lhs.indptr.itemsize // 4) + lhs.indices.nbytes // (lhs.indices.itemsize // 4) + lhs.data.nbytes + rhs.nbytes
+    h2d_values_only = lhs.data.nbytes + rhs.nbytes  # the pattern is compared on the host and not re-sent
+    d2h = x.nbytes
+
+    # ---- roofline of the dominant kernel: fine-level Jacobi sweep, per-launch CUDA events
+    b.set_option("profile", 1)
+    b.reset_kernel_profile()
+    for _ in range(min(args.steps, 5)):
+        b.solve_staged()
+    b.set_option("profile", 0)
+    jac_ms, jac_launches = b.kernel_profile(0, 0)
+    kinds = {0: "jacobi", 1: "residual", 2: "restrict", 3: "prolong_add", 4: "norm", 5: "coarse_solve"}
+    per_kernel = {}
+    for kind, name in kinds.items():
+        for lvl in range(len(info)):
+            ms, cnt = b.kernel_profile(kind, lvl)
+            if cnt:
+                per_kernel[f"{name}_L{lvl}"] = {"us": 1e3 * ms / cnt, "launches": cnt}
+    nnz0, n0 = info[0]["nnz_a"], info[0]["rows"]
+    jac_bytes = nnz0 * 12 + n0 * 36
+    jac_us = 1e3 * jac_ms / max(jac_launches, 1)
+    peak, peak_src = measured_hbm_peak()
+    achieved = jac_bytes / (jac_us * 1e-6) / 1e9 if jac_us > 0 else 0.0
+    vcycle_bytes = 0
+    for lvl, lv in enumerate(info[:-1]):
+        nn, nz, nu, nc = lv["rows"], lv["nnz_a"], lv["nnz_u"], info[lvl + 1]["rows"]
+        vcycle_bytes += 4 * (nz * 12 + nn * 36) + (nz * 12 + nn * 28) + (nu * 12 + nc * 12 + nn * 8) + (nu * 12 + nn * 20 + nc * 8)
+    vcycle_bytes += info[-1]["rows"] ** 2 * 8
+    roofline = {"bound": "hbm", "kernel": "spmv_staged_kernel<double,1,EPI_JACOBI> (fine level)" if args.kernel_path == 0 else "spmv_direct_kernel<double,1,EPI_JACOBI> (fine level)",
+                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "algorithmic_bytes_per_launch": jac_bytes, "us_per_launch": jac_us,
+                "launches_timed": jac_launches,
+                "vcycle_algorithmic_bytes": vcycle_bytes,
+                "vcycle_frac": (vcycle_bytes / ((cyc_ms / max(cycles, 1)) * 1e-3) / 1e9) / peak if cycles else None}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_values_only), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "note": f"host CSR pattern ({h2d - h2d_values_only} B) is compared against the staged one on the host and not re-sent"},
+            "gpu_launches": int(launches), "roofline": roofline,
+            "smoother": f"damped Jacobi omega={args.omega:.4f}", "cycles_per_step": cycles / args.steps,
+            "cycles_only_vcycles_per_s": cycles / (cyc_ms / 1e3), "time_to_tol_s": dev_ms / args.steps / 1e3,
+            "residue": residue, "wall_s_timed_region": wall, "last_step_split_ms": split, "per_kernel_us": per_kernel,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(V, neigh, M, lhs, rhs, U, args.tol, 1, 0)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": "one full solve to the same tolerance, lexicographic Gauss-Seidel (reference algorithm), same U",
+                                    "time_to_tol_s": r["full_solve_s"], "cycles_to_tol": r["full_solve_cycles"],
+                                    "cycles_only_vcycles_per_s": r["cycles_only_value"], "host_cpus": os.cpu_count()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -40,10 +40,12 @@ class Weighting(enum.IntEnum):
     INVDIST = 2
 
 
-def _csr_arrays(m):
+def _csr_arrays(m, n=None):
     """(indptr int32, indices int32, data f64) of a scipy matrix, converting to CSR if needed."""
     if not sp.issparse(m):
         raise TypeError("expected a scipy.sparse matrix")
+    if n is not None and m.shape != (n, n):
+        raise ValueError(f"expected a {n} x {n} matrix, got {m.shape}")
     m = m.tocsr()
     if m.nnz >= 2**31:
         raise ValueError("matrices with 2^31 or more stored entries are not supported")
@@ -113,14 +115,14 @@ class MultigridSolver:
 
     # ------------------------------------------------------------------ the hot path
     def solve(self, lhs, rhs):
-        ap, ai, ad = _csr_arrays(lhs)
+        ap, ai, ad = _csr_arrays(lhs, self._n)
         b = _dense_rhs(rhs, self._n)
         x = np.empty_like(b)
         check(self._h, lib.gmg_solve(self._h, self._n, i32(ap), i32(ai), f64(ad), f64(b), f64(x), b.shape[1]))
         return x
 
     def residual(self, lhs, rhs, solution, type=2):
-        ap, ai, ad = _csr_arrays(lhs)
+        ap, ai, ad = _csr_arrays(lhs, self._n)
         b = _dense_rhs(rhs, self._n)
         x = _dense_rhs(solution, self._n)
         if x.shape != b.shape:
@@ -131,7 +133,7 @@ class MultigridSolver:
 
     # split form used by the benchmark to keep the system resident in HBM
     def stage(self, lhs, rhs):
-        ap, ai, ad = _csr_arrays(lhs)
+        ap, ai, ad = _csr_arrays(lhs, self._n)
         b = _dense_rhs(rhs, self._n)
         self._staged_shape = b.shape
         check(self._h, lib.gmg_stage_system(self._h, self._n, i32(ap), i32(ai), f64(ad), f64(b), b.shape[1]))
@@ -264,6 +266,34 @@ class MultigridSolver:
                 break
             out.append({"rows": rows.value, "nnz_a": nnz_a.value, "nnz_u": nnz_u.value})
             k += 1
+        return out
+
+    def level_matrix(self, level):
+        """Operator of ``level`` as held on the device (0: lhs, k >= 1: Galerkin), scipy CSR."""
+        info = self.level_info()[level]
+        indptr = np.empty(info["rows"] + 1, dtype=np.int32)
+        indices = np.empty(info["nnz_a"], dtype=np.int32)
+        data = np.empty(info["nnz_a"], dtype=np.float64)
+        check(self._h, lib.gmg_get_level_matrix(self._h, int(level), i32(indptr), i32(indices), f64(data)))
+        return sp.csr_matrix((data, indices, indptr), shape=(info["rows"], info["rows"]))
+
+    OPS = {"jacobi": 0, "residual": 1, "restrict": 2, "prolong_add": 3, "coarse": 5}
+
+    def level_op(self, kind, level, a, b=None, sweeps=1):
+        """One V-cycle operator on host vectors (gmg_level_op); needs ``stage`` first."""
+        rows = [lv["rows"] for lv in self.level_info()]
+        K = self._staged_shape[1]
+        kind = self.OPS[kind] if isinstance(kind, str) else int(kind)
+        n_in = rows[level + 1] if kind == 3 else rows[level]
+        n_out = rows[level + 1] if kind == 2 else rows[level]
+        a = _dense_rhs(a, n_in)
+        if a.shape[1] != K:
+            raise ValueError(f"vectors must have the staged K = {K} columns")
+        bb = None
+        if b is not None:
+            bb = _dense_rhs(b, rows[level])
+        out = np.empty((n_out, K))
+        check(self._h, lib.gmg_level_op(self._h, kind, int(level), f64(a), f64(bb) if bb is not None else None, f64(out), int(sweeps)))
         return out
 
     def kernel_profile(self, kind, level=-1):

@@ -345,6 +345,24 @@ int gmg_level_info(gmg_handle h, int32_t level, int64_t* rows, int64_t* nnz_a, i
     });
 }
 
+int gmg_level_op(gmg_handle h, int32_t kind, int32_t level, const double* a, const double* b, double* out, int32_t sweeps) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(out != nullptr, "null argument");
+        require(h->s.engine != nullptr, "gmg_level_op needs a staged system (gmg_stage_system)");
+        h->s.engine->level_op(kind, level, a, b, out, sweeps);
+    });
+}
+
+int gmg_get_level_matrix(gmg_handle h, int32_t level, int32_t* indptr, int32_t* indices, double* data) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(indptr && indices && data, "null argument");
+        require(h->s.engine != nullptr, "no system staged on the device");
+        h->s.engine->get_level_matrix(level, indptr, indices, data);
+    });
+}
+
 int gmg_kernel_profile(gmg_handle h, int32_t kind, int32_t level, double* total_ms, int64_t* launches) {
     if (!h) return 1;
     return guarded(h, [&] {

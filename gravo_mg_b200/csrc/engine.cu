@@ -138,6 +138,7 @@ public:
                           std::memcmp(a_indices_h_.data(), indices, nnz * sizeof(int)) == 0;
         if (!same) setup_pattern(n, indptr, indices);
         lv_[0].A.upload_values(data, stream_);
+        numeric_ready_ = false;
         if (K != K_) {
             K_ = K;
             allocate_vectors();
@@ -166,7 +167,6 @@ public:
         if (p.cycle_type != 0) throw std::invalid_argument("only cycle_type 0 (V-cycle) is implemented on the device path");
         if (p.max_iter < 1) throw std::invalid_argument("max_iter must be >= 1");
         if (p.stopping_criteria < 0 || p.stopping_criteria > 3) throw std::invalid_argument("stopping_criteria must be 0..3");
-        const int L = n_levels_;
         if (hist_res_.count < (size_t)p.max_iter) {
             drop_graphs();  // captured launches hold the old history pointers
             hist_res_.ensure(p.max_iter);
@@ -180,30 +180,7 @@ public:
         // x0 = rhs (core.cpp:69), b = rhs
         set_initial_guess();
         launches += sizeof(T) == 4 ? 2 : 0;
-
-        // ---- "reduction": Abar[k+1] = U[k]^T Abar[k] U[k] (multigrid_solver.cpp:1387-1392)
-        launch_extract_dinv<T>(lv_[0].n, lv_[0].A.indptr.ptr, lv_[0].A.indices.ptr, lv_[0].A.v64.ptr, lv_[0].dinv.ptr, ctl_.ptr, stream_);
-        lv_[0].A.refresh_cast(stream_);
-        ++launches;
-        for (int k = 0; k < L; ++k) {
-            Level& f = lv_[k];
-            Level& c = lv_[k + 1];
-            launch_spgemm_numeric(f.AP.nnz, f.AP.rowidx.ptr, f.AP.indices.ptr, f.AP.v64.ptr, f.A.indptr.ptr, f.A.indices.ptr,
-                                  f.A.v64.ptr, f.P.indptr.ptr, f.P.indices.ptr, f.P.v64.ptr, stream_);
-            launch_spgemm_numeric(c.A.nnz, c.A.rowidx.ptr, c.A.indices.ptr, c.A.v64.ptr, f.R.indptr.ptr, f.R.indices.ptr,
-                                  f.R.v64.ptr, f.AP.indptr.ptr, f.AP.indices.ptr, f.AP.v64.ptr, stream_);
-            launches += 2;
-            if (k + 1 < L) {
-                launch_extract_dinv<T>(c.n, c.A.indptr.ptr, c.A.indices.ptr, c.A.v64.ptr, c.dinv.ptr, ctl_.ptr, stream_);
-                c.A.refresh_cast(stream_);
-                ++launches;
-            }
-        }
-        GMG_CUDA(cudaEventRecord(ev_[1], stream_));
-
-        // ---- "coarsest_solve": factor Abar[L] (multigrid_solver.cpp:1401)
-        coarse_.factor(lv_[L].A.indptr.ptr, lv_[L].A.indices.ptr, lv_[L].A.v64.ptr, ctl_.ptr, stream_);
-        launches += coarse_.launches_per_factor();
+        launches += setup_numeric(ev_[1]);
         GMG_CUDA(cudaEventRecord(ev_[2], stream_));
 
         // ---- "cycles" (multigrid_solver.cpp:1411-1417)
@@ -293,6 +270,155 @@ public:
         GMG_CUDA(cudaMemcpyAsync(ctl_host_, aux, sizeof(CycleControl), cudaMemcpyDeviceToHost, stream_));
         GMG_CUDA(cudaStreamSynchronize(stream_));
         return ctl_host_->residue;
+    }
+
+
+    // "reduction" (multigrid_solver.cpp:1387-1392) and "coarsest_solve" factorisation (:1401) from
+    // the values of A staged on the device. Returns the number of kernel launches.
+    int64_t setup_numeric(cudaEvent_t after_reduction) {
+        const int L = n_levels_;
+        int64_t launches = 0;
+        if (L > 0) {
+            launch_extract_dinv<T>(lv_[0].n, lv_[0].A.indptr.ptr, lv_[0].A.indices.ptr, lv_[0].A.v64.ptr, lv_[0].dinv.ptr, ctl_.ptr, stream_);
+            ++launches;
+        }
+        lv_[0].A.refresh_cast(stream_);
+        launches += sizeof(T) == 4 ? 1 : 0;
+        for (int k = 0; k < L; ++k) {
+            Level& f = lv_[k];
+            Level& c = lv_[k + 1];
+            launch_spgemm_numeric(f.AP.nnz, f.AP.rowidx.ptr, f.AP.indices.ptr, f.AP.v64.ptr, f.A.indptr.ptr, f.A.indices.ptr,
+                                  f.A.v64.ptr, f.P.indptr.ptr, f.P.indices.ptr, f.P.v64.ptr, stream_);
+            launch_spgemm_numeric(c.A.nnz, c.A.rowidx.ptr, c.A.indices.ptr, c.A.v64.ptr, f.R.indptr.ptr, f.R.indices.ptr,
+                                  f.R.v64.ptr, f.AP.indptr.ptr, f.AP.indices.ptr, f.AP.v64.ptr, stream_);
+            launches += 2;
+            if (k + 1 < L) {
+                launch_extract_dinv<T>(c.n, c.A.indptr.ptr, c.A.indices.ptr, c.A.v64.ptr, c.dinv.ptr, ctl_.ptr, stream_);
+                c.A.refresh_cast(stream_);
+                launches += sizeof(T) == 4 ? 2 : 1;
+            }
+        }
+        if (after_reduction) GMG_CUDA(cudaEventRecord(after_reduction, stream_));
+        coarse_.factor(lv_[L].A.indptr.ptr, lv_[L].A.indices.ptr, lv_[L].A.v64.ptr, ctl_.ptr, stream_);
+        launches += coarse_.launches_per_factor();
+        numeric_ready_ = true;
+        return launches;
+    }
+
+    void check_setup_errors() {
+        GMG_CUDA(cudaMemcpyAsync(ctl_host_, ctl_.ptr, sizeof(CycleControl), cudaMemcpyDeviceToHost, stream_));
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+        if (ctl_host_->error & 1) throw std::runtime_error("an operator has a missing, non-positive or non-finite diagonal entry (Jacobi smoother needs A_ii > 0)");
+        if (ctl_host_->error & 4) throw std::runtime_error("coarsest-level Cholesky broke down: the Galerkin operator is not positive definite");
+    }
+
+    // ------------------------------------------------------------------ single operators
+    // One operator of the V-cycle on caller-supplied vectors (parity tests and per-kernel
+    // measurement); uses the level's own device buffers, so it discards a previous solution.
+    void level_op(int kind, int level, const double* a, const double* b, double* out, int sweeps) override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        if (!staged_) throw std::logic_error("level_op before stage_system");
+        const int L = n_levels_;
+        if (level < 0 || level > L) throw std::invalid_argument("level out of range");
+        if (cycle_dirty_) build_cycle();
+        if (!numeric_ready_) {
+            GMG_CUDA(cudaMemsetAsync(ctl_.ptr, 0, sizeof(CycleControl), stream_));
+            setup_numeric(nullptr);
+            check_setup_errors();
+        }
+        solved_ = false;
+        GMG_CUDA(cudaMemsetAsync(ctl_.ptr, 0, sizeof(CycleControl), stream_));  // done = 0
+        io64_.ensure((size_t)st_->n * K_);
+        auto up = [&](T* dst, const double* src, size_t count) {
+            if (sizeof(T) == 8) {
+                GMG_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyHostToDevice, stream_));
+            } else {
+                GMG_CUDA(cudaMemcpyAsync(io64_.ptr, src, count * sizeof(double), cudaMemcpyHostToDevice, stream_));
+                launch_cast_f64_f32(io64_.ptr, reinterpret_cast<float*>(dst), count, stream_);
+                GMG_CUDA(cudaStreamSynchronize(stream_));
+            }
+        };
+        auto down = [&](const T* src, size_t count) {
+            if (sizeof(T) == 8) {
+                GMG_CUDA(cudaMemcpyAsync(out, src, count * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+            } else {
+                launch_cast_f32_f64(reinterpret_cast<const float*>(src), io64_.ptr, count, stream_);
+                GMG_CUDA(cudaMemcpyAsync(out, io64_.ptr, count * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+            }
+            GMG_CUDA(cudaStreamSynchronize(stream_));
+        };
+        Level& f = lv_[level];
+        const size_t nf = (size_t)f.n * K_;
+        Op op;
+        op.level = level;
+        switch (kind) {
+            case OP_JACOBI: {
+                if (level >= L) throw std::invalid_argument("the coarsest level has no smoother");
+                if (!a || !b) throw std::invalid_argument("jacobi needs x and b");
+                up(f.x.ptr, a, nf), up(f.b.ptr, b, nf);
+                T* cur = f.x.ptr;
+                T* alt = f.t.ptr;
+                op.kind = OP_JACOBI, op.epi = EPI_JACOBI, op.plan = &f.A.plan, op.args = base_args(f.A);
+                for (int i = 0; i < sweeps; ++i) {
+                    op.args.x = cur, op.args.b = f.b.ptr, op.args.dinv = f.dinv.ptr, op.args.out = alt;
+                    run_op(op, stream_, 0);
+                    std::swap(cur, alt);
+                }
+                down(cur, nf);
+                break;
+            }
+            case OP_RESIDUAL: {
+                if (!a || !b) throw std::invalid_argument("residual needs x and b");
+                up(f.x.ptr, a, nf), up(f.b.ptr, b, nf);
+                op.kind = OP_RESIDUAL, op.epi = EPI_RESIDUAL, op.plan = &f.A.plan, op.args = base_args(f.A);
+                op.args.x = f.x.ptr, op.args.b = f.b.ptr, op.args.out = f.r.ptr;
+                run_op(op, stream_, 0);
+                down(f.r.ptr, nf);
+                break;
+            }
+            case OP_RESTRICT: {
+                if (level >= L) throw std::invalid_argument("no prolongation below the coarsest level");
+                if (!a) throw std::invalid_argument("restrict needs r");
+                up(f.r.ptr, a, nf);
+                op.kind = OP_RESTRICT, op.epi = EPI_SPMV, op.plan = &f.R.plan, op.args = base_args(f.R);
+                op.args.x = f.r.ptr, op.args.out = lv_[level + 1].b.ptr;
+                run_op(op, stream_, 0);
+                down(lv_[level + 1].b.ptr, (size_t)lv_[level + 1].n * K_);
+                break;
+            }
+            case OP_PROLONG: {
+                if (level >= L) throw std::invalid_argument("no prolongation below the coarsest level");
+                if (!a || !b) throw std::invalid_argument("prolong_add needs eps and x");
+                up(lv_[level + 1].x.ptr, a, (size_t)lv_[level + 1].n * K_), up(f.x.ptr, b, nf);
+                op.kind = OP_PROLONG, op.epi = EPI_ADD, op.plan = &f.P.plan, op.args = base_args(f.P);
+                op.args.x = lv_[level + 1].x.ptr, op.args.xin = f.x.ptr, op.args.out = f.t.ptr;
+                run_op(op, stream_, 0);
+                down(f.t.ptr, nf);
+                break;
+            }
+            case OP_COARSE: {
+                if (level != L) throw std::invalid_argument("the direct solve lives on the coarsest level");
+                if (!a) throw std::invalid_argument("coarse_solve needs b");
+                up(f.b.ptr, a, nf);
+                op.kind = OP_COARSE;
+                run_op(op, stream_, 0);
+                down(f.x.ptr, nf);
+                break;
+            }
+            default:
+                throw std::invalid_argument("unknown operator kind");
+        }
+    }
+
+    void get_level_matrix(int level, int* indptr, int* indices, double* data) override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        if (!pattern_ready_ || level < 0 || level > n_levels_) throw std::invalid_argument("no such level staged on the device");
+        if (level > 0 && !numeric_ready_) throw std::logic_error("Galerkin operators exist after a solve or a level_op");
+        const DevMat<T>& m = lv_[level].A;
+        GMG_CUDA(cudaMemcpyAsync(indptr, m.indptr.ptr, ((size_t)m.rows + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        GMG_CUDA(cudaMemcpyAsync(indices, m.indices.ptr, (size_t)m.nnz * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        GMG_CUDA(cudaMemcpyAsync(data, m.v64.ptr, (size_t)m.nnz * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        GMG_CUDA(cudaStreamSynchronize(stream_));
     }
 
     bool level_info(int level, int64_t* rows, int64_t* nnz_a, int64_t* nnz_u) override {
@@ -684,12 +810,13 @@ private:
     DenseCoarseSolver coarse_;
     DeviceBuffer<CycleControl> ctl_;
     CycleControl* ctl_host_ = nullptr;
-    DeviceBuffer<double> hist_res_, hist_ms_, partials_, mass_, minv_, rhs64_, x64_, coarse_b64_, coarse_x64_;
+    DeviceBuffer<double> hist_res_, hist_ms_, partials_, mass_, minv_, rhs64_, x64_, coarse_b64_, coarse_x64_, io64_;
     DeviceBuffer<int> q_indptr_, q_indices_;
     DeviceBuffer<double> q_vals_, q_b_, q_x_;
     std::vector<int> a_indptr_h_, a_indices_h_;
     std::vector<HostCsr> r_host_;
     bool hierarchy_ready_ = false, pattern_ready_ = false, staged_ = false, solved_ = false, cycle_dirty_ = true;
+    bool numeric_ready_ = false;
     std::vector<Op> ops_;
     T* x_final_ = nullptr;
     int launches_per_cycle_ = 0;

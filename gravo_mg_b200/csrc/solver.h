@@ -23,6 +23,8 @@ public:
     virtual void fetch_solution(double* x_out) = 0;
     virtual double residual(int64_t n, const int* indptr, const int* indices, const double* data, const double* rhs,
                             const double* x, int K, int type) = 0;
+    virtual void level_op(int kind, int level, const double* a, const double* b, double* out, int sweeps) = 0;
+    virtual void get_level_matrix(int level, int* indptr, int* indices, double* data) = 0;
     virtual void invalidate_hierarchy() = 0;
     virtual void invalidate_cycle() = 0;
     virtual bool level_info(int level, int64_t* rows, int64_t* nnz_a, int64_t* nnz_u) = 0;

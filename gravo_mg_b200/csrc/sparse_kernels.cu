@@ -44,18 +44,23 @@ __global__ void norm_finalize_kernel(const double* __restrict__ partials, NormCh
     if (threadIdx.x == 0) {
         const int K = n_sums / 2;
         double residue = 0.0;
+        bool diverged = false;
         if (ctl->criterion == 3) {
             double tot = 0.0;
             for (int k = 0; k < K; ++k) tot += sums[2 * k];
             residue = sqrt(tot);
+            diverged = !(residue <= 1.7976931348623157e308);
         } else {
             for (int k = 0; k < K; ++k) {  // maxCoeff over the right-hand sides
                 const double rk = sqrt(sums[2 * k] / sums[2 * k + 1]);
                 if (k == 0 || rk > residue || rk != rk) residue = rk;
+                // 0/0 (an all-zero right-hand side) is NaN upstream too and simply ends the loop;
+                // a non-finite residual of a non-zero system means the smoother diverged
+                if (!(rk <= 1.7976931348623157e308) && sums[2 * k + 1] > 0.0) diverged = true;
             }
         }
         ctl->residue = residue;
-        if (residue != residue) ctl->error |= 2;
+        if (diverged) ctl->error |= 2;
         if (record) {
             const int it = ctl->iter;
             hist_res[it] = residue;

@@ -120,9 +120,10 @@ def cotangent_stiffness(V, F, fmt: str = "csc"):
     rows = np.concatenate([ii, jj, ii, jj])
     cols = np.concatenate([jj, ii, ii, jj])
     vals = np.concatenate([-w, -w, w, w])
-    S = sp.coo_matrix((vals, (rows, cols)), shape=(n, n))
-    S = S.tocsc() if fmt == "csc" else S.tocsr()
+    S = sp.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsr()
     S.sum_duplicates()
+    S = (S + S.T) * 0.5  # bitwise symmetric whatever order the duplicates were summed in
+    S = S.tocsc() if fmt == "csc" else S.tocsr()
     S.sort_indices()
     return S
 

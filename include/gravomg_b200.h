@@ -126,6 +126,20 @@ int gmg_get_convergence(gmg_handle h, double* t_ms, double* residue, int32_t* co
 /* ---- measurement support (not part of the reference surface) ----
  * Level sizes of the operators staged on the device: rows and stored entries of A_k, and of U_k. */
 int gmg_level_info(gmg_handle h, int32_t level, int64_t* rows, int64_t* nnz_a, int64_t* nnz_u);
+/* CSR of the operator of a level as the device holds it (level 0: the staged lhs; k >= 1: the
+ * Galerkin operator Abar[k], multigrid_solver.cpp:1389-1391). Sizes from gmg_level_info. */
+int gmg_get_level_matrix(gmg_handle h, int32_t level, int32_t* indptr, int32_t* indices, double* data);
+/* One operator of the V-cycle (multigrid_solver.cpp:1059-1088) on caller-supplied host vectors,
+ * for op-level parity tests and per-kernel measurement. Needs gmg_stage_system first (K of the
+ * staged right-hand side is the K of every vector here); computes the Galerkin chain and the
+ * coarse factor if the staged values have not been reduced yet. n_k x K row-major, fp64.
+ *   kind 0 jacobi      a = x, b = rhs       out = x after `sweeps` sweeps              (level < L)
+ *   kind 1 residual    a = x, b = rhs       out = rhs - A_k x
+ *   kind 2 restrict    a = r (n_k)          out = U_k^T r (n_{k+1})                    (level < L)
+ *   kind 3 prolong_add a = eps (n_{k+1}), b = x (n_k)   out = x + U_k eps              (level < L)
+ *   kind 5 coarse      a = rhs (n_L)        out = Abar[L]^-1 rhs                       (level = L) */
+int gmg_level_op(gmg_handle h, int32_t kind, int32_t level, const double* a, const double* b, double* out,
+                 int32_t sweeps);
 /* Per-kernel device time accumulated while option "profile" = 1. Kernel kinds:
  * 0 jacobi, 1 residual, 2 restrict, 3 prolong_add, 4 norm, 5 coarse_solve. Level -1 sums levels. */
 int gmg_kernel_profile(gmg_handle h, int32_t kind, int32_t level, double* total_ms, int64_t* launches);
