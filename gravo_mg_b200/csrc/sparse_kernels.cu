@@ -174,7 +174,15 @@ int resident_blocks(const void* kernel, int threads, size_t smem) {
     auto key = std::make_pair(kernel, smem);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
-    if (smem > 48 * 1024) GMG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem_limit()));
+    static std::map<const void*, bool> opted_in;
+    if (smem > 48 * 1024 && !opted_in[kernel]) {
+        // opt in once per kernel to everything the device allows beyond its static shared memory
+        cudaFuncAttributes attr;
+        GMG_CUDA(cudaFuncGetAttributes(&attr, kernel));
+        GMG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(staged_smem_limit() - attr.sharedSizeBytes)));
+        opted_in[kernel] = true;
+    }
     int nb = 0;
     GMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem));
     if (nb < 1) nb = 1;
@@ -245,6 +253,7 @@ template int launch_spmv<float>(int, int, SpmvArgs<float>, const SpmvPlan&, cuda
 
 void launch_norm_finalize(const double* partials, const NormChunks& chunks, CycleControl* ctl, double* hist_res,
                           double* hist_ms, int record, unsigned long long cond_handle, cudaStream_t stream) {
+    if (g_dry_run) return;
     norm_finalize_kernel<<<1, 256, 0, stream>>>(partials, chunks, ctl, hist_res, hist_ms, record, cond_handle);
     GMG_CUDA(cudaGetLastError());
 }
