@@ -161,8 +161,13 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-6)
     ap.add_argument("--lower-bound", type=int, default=500)
     ap.add_argument("--omega", type=float, default=2.0 / 3.0)
+    ap.add_argument("--smoother", default="chebyshev", choices=["chebyshev", "jacobi"])
+    ap.add_argument("--cheb-alpha", type=float, default=10.0)
+    ap.add_argument("--sweeps", type=int, default=2, help="pre and post sweeps per level")
+    ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--loop-mode", type=int, default=1)
     ap.add_argument("--kernel-path", type=int, default=0)
+    ap.add_argument("--use-graph", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -172,7 +177,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n_side = args.n_side
     workload = (f"torus {n_side}x{n_side} ({n_side * n_side} vertices) Poisson lhs=1e-6*M+S, fp64, K=1, "
-                f"V-cycle 2+2 sweeps, lower_bound={args.lower_bound}, tol={args.tol:g} (criterion 2, M-norm)")
+                f"V-cycle {args.sweeps}+{args.sweeps} sweeps, lower_bound={args.lower_bound}, tol={args.tol:g} (criterion 2, M-norm)")
     config = {"workload": workload, "config_index": 1, "levels": None,
               "l2": "operators + vectors of one solve (~250 MB at 1M vertices) exceed the 126 MB L2; a 512 MB buffer is also written between timed steps",
               "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one system per GPU, no collective)"}
@@ -217,10 +222,13 @@ def main():
     V, neigh, M, lhs, rhs = build_problem(n_side)
     n = lhs.shape[0]
     solver = gravomg.MultigridSolver(V, neigh, M, lower_bound=args.lower_bound, tolerance=args.tol, max_iter=100,
-                                     omega=args.omega, device=local_rank)
+                                     pre_iters=args.sweeps, post_iters=args.sweeps, smoother=args.smoother,
+                                     omega=args.omega, cheb_alpha=args.cheb_alpha, device=local_rank)
     b = solver.solver
     b.set_option("loop_mode", args.loop_mode)
     b.set_option("kernel_path", args.kernel_path)
+    b.set_option("use_graph", args.use_graph)
+    b.set_option("lanes", args.lanes)
     U = solver.prolongation_matrices
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
@@ -310,9 +318,9 @@ def main():
     vcycle_bytes = 0
     for lvl, lv in enumerate(info[:-1]):
         nn, nz, nu, nc = lv["rows"], lv["nnz_a"], lv["nnz_u"], info[lvl + 1]["rows"]
-        vcycle_bytes += 4 * (nz * 12 + nn * 36) + (nz * 12 + nn * 28) + (nu * 12 + nc * 12 + nn * 8) + (nu * 12 + nn * 20 + nc * 8)
+        vcycle_bytes += 2 * args.sweeps * (nz * 12 + nn * 36) + (nz * 12 + nn * 28) + (nu * 12 + nc * 12 + nn * 8) + (nu * 12 + nn * 20 + nc * 8)
     vcycle_bytes += info[-1]["rows"] ** 2 * 8
-    roofline = {"bound": "hbm", "kernel": "spmv_staged_kernel<double,1,EPI_JACOBI> (fine level)" if args.kernel_path == 0 else "spmv_direct_kernel<double,1,EPI_JACOBI> (fine level)",
+    roofline = {"bound": "hbm", "kernel": "spmv_staged_kernel<double,1,EPI_JACOBI,LANES> (fine level)" if args.kernel_path == 0 else "spmv_direct_kernel<double,1,EPI_JACOBI,LANES> (fine level)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "algorithmic_bytes_per_launch": jac_bytes, "us_per_launch": jac_us,
                 "launches_timed": jac_launches,
@@ -328,7 +336,9 @@ def main():
                     "ms_per_step": 1e3 * e2e_s / args.steps,
                     "note": f"host CSR pattern ({h2d - h2d_values_only} B) is compared against the staged one on the host and not re-sent"},
             "gpu_launches": int(launches), "roofline": roofline,
-            "smoother": f"damped Jacobi omega={args.omega:.4f}", "cycles_per_step": cycles / args.steps,
+            "smoother": (f"Chebyshev-weighted Jacobi, band rho/{args.cheb_alpha:g}..rho" if args.smoother == "chebyshev"
+                         else f"damped Jacobi omega={args.omega:.4f}") + f", {args.sweeps}+{args.sweeps} sweeps",
+            "cycles_per_step": cycles / args.steps,
             "cycles_only_vcycles_per_s": cycles / (cyc_ms / 1e3), "time_to_tol_s": dev_ms / args.steps / 1e3,
             "residue": residue, "wall_s_timed_region": wall, "last_step_split_ms": split, "per_kernel_us": per_kernel,
         }

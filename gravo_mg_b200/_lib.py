@@ -42,6 +42,7 @@ class GmgParams(C.Structure):
         ("dtype", C.c_int32),
         ("device", C.c_int32),
         ("build_hierarchy", C.c_int32),
+        ("cheb_alpha", C.c_double),
     ]
 
 
@@ -77,6 +78,7 @@ SIGNATURES = {
     "gmg_get_timing": (C.c_int, [_h, C.c_int32, C.c_char_p, _f64p]),
     "gmg_get_convergence": (C.c_int, [_h, _f64p, _f64p, _i32p]),
     "gmg_level_info": (C.c_int, [_h, C.c_int32, _i64p, _i64p, _i64p]),
+    "gmg_get_smoother_weights": (C.c_int, [_h, C.c_int32, _f64p, _f64p, _f64p]),
     "gmg_get_level_matrix": (C.c_int, [_h, C.c_int32, _i32p, _i32p, _f64p]),
     "gmg_level_op": (C.c_int, [_h, C.c_int32, C.c_int32, _f64p, _f64p, _f64p, C.c_int32]),
     "gmg_kernel_profile": (C.c_int, [_h, C.c_int32, C.c_int32, _f64p, _i64p]),

@@ -69,7 +69,8 @@ class MultigridSolver:
     def __init__(self, positions, neighbors, mass, ratio, low_bound, cycle_type, tolerance, stopping_criteria,
                  pre_iters, post_iters, max_iter, check_voronoi, nested, sampling_strategy, weighting, sig06,
                  normals, verbose, debug, ablation, ablation_num_points, ablation_random,
-                 *, omega=2.0 / 3.0, dtype="float64", device=0, build_hierarchy=True):
+                 *, smoother="chebyshev", omega=2.0 / 3.0, cheb_alpha=10.0, dtype="float64", device=0,
+                 build_hierarchy=True):
         self._h = C.c_void_p()
         pos = as_f64(positions)
         if pos.ndim != 2 or pos.shape[1] != 3:
@@ -88,6 +89,9 @@ class MultigridSolver:
         p.sig06, p.verbose, p.debug = int(bool(sig06)), int(bool(verbose)), int(bool(debug))
         p.ablation, p.ablation_num_points, p.ablation_random = int(bool(ablation)), int(ablation_num_points), int(bool(ablation_random))
         p.omega = float(omega)
+        p.smoother = {"jacobi": 0, "chebyshev": 1}[smoother] if isinstance(smoother, str) else int(smoother)
+        p.cheb_alpha = float(cheb_alpha)
+        self._sweeps = (int(pre_iters), int(post_iters))
         p.dtype = {"float64": 0, "fp64": 0, "f64": 0, "float32": 1, "fp32": 1, "f32": 1}[str(np.dtype(dtype)) if not isinstance(dtype, str) else dtype]
         p.device = int(device)
         p.build_hierarchy = int(bool(build_hierarchy))
@@ -276,6 +280,16 @@ class MultigridSolver:
         data = np.empty(info["nnz_a"], dtype=np.float64)
         check(self._h, lib.gmg_get_level_matrix(self._h, int(level), i32(indptr), i32(indices), f64(data)))
         return sp.csr_matrix((data, indices, indptr), shape=(info["rows"], info["rows"]))
+
+    def smoother_weights(self, level):
+        """(rho, pre, post): Gershgorin bound of D^-1 A_level and the Jacobi dampings per sweep."""
+        pre_n = int(self.get_option("pre_iters"))
+        post_n = int(self.get_option("post_iters"))
+        rho = C.c_double()
+        pre = np.zeros(max(pre_n, 1))
+        post = np.zeros(max(post_n, 1))
+        check(self._h, lib.gmg_get_smoother_weights(self._h, int(level), C.byref(rho), f64(pre), f64(post)))
+        return rho.value, pre[:pre_n].copy(), post[:post_n].copy()
 
     OPS = {"jacobi": 0, "residual": 1, "restrict": 2, "prolong_add": 3, "coarse": 5}
 

@@ -2,8 +2,13 @@
 defaults (gravomg_bindings/src/gravomg/core.py:8-147), running on the B200 path.
 
 Keyword-only additions (defaults keep every reference call site working):
-    omega   Jacobi damping of the device smoother (the reference's lexicographic Gauss-Seidel
-            is sequential; the device path substitutes damped Jacobi)
+    smoother    'chebyshev' (default) or 'jacobi'. The reference's lexicographic Gauss-Seidel is
+                sequential; the device path substitutes Jacobi sweeps x += w D^-1 (b - A x). With
+                'chebyshev' the dampings of the pre_iters (post_iters) sweeps are the inverse roots
+                of the Chebyshev polynomial on [rho/cheb_alpha, rho] of D^-1 A (see DESIGN.md);
+                with 'jacobi' every sweep uses ``omega``.
+    omega       damping of the 'jacobi' smoother
+    cheb_alpha  width of the band the 'chebyshev' smoother damps
     dtype   'float64' (default) or 'float32' smoother levels
     device  CUDA device ordinal
 """
@@ -21,7 +26,7 @@ class MultigridSolver(object):
         ratio=8.0, lower_bound=1000, cycle_type=0, tolerance=1e-4, stopping_criteria=2, pre_iters=2, post_iters=2, max_iter=100,
         check_voronoi=True, nested=False, sampling_strategy=Sampling.FASTDISK, weighting=Weighting.BARYCENTRIC,
         sig06=False, normals=None, verbose=False, debug=False, ablation=False, ablation_num_points=3, ablation_random=False,
-        *, omega=2.0 / 3.0, dtype="float64", device=0, build_hierarchy=True,
+        *, smoother="chebyshev", omega=2.0 / 3.0, cheb_alpha=10.0, dtype="float64", device=0, build_hierarchy=True,
     ):
         """Creates the Gravo MG solver for linear systems on curved surfaces (meshes and point clouds).
 
@@ -38,7 +43,8 @@ class MultigridSolver(object):
             ratio, lower_bound, cycle_type, tolerance, stopping_criteria, pre_iters, post_iters, max_iter,
             check_voronoi, nested, sampling_strategy, weighting,
             sig06, normals, verbose, debug, ablation, ablation_num_points, ablation_random,
-            omega=omega, dtype=dtype, device=device, build_hierarchy=build_hierarchy,
+            smoother=smoother, omega=omega, cheb_alpha=cheb_alpha, dtype=dtype, device=device,
+            build_hierarchy=build_hierarchy,
         )
         self.sig21_computed = False
         self.sig21bary_computed = False

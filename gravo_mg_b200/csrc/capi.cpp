@@ -74,7 +74,8 @@ int gmg_default_params(gmg_params* p) {
     p->sampling_strategy = GMG_SAMPLING_FASTDISK;
     p->weighting = GMG_WEIGHTING_BARYCENTRIC;
     p->ablation_num_points = 3;
-    p->smoother = GMG_SMOOTHER_JACOBI;
+    p->smoother = GMG_SMOOTHER_CHEBYSHEV;
+    p->cheb_alpha = 10.0;
     p->omega = 2.0 / 3.0;
     p->dtype = GMG_DTYPE_F64;
     p->device = 0;
@@ -93,7 +94,9 @@ int gmg_create(const gmg_params* p, int64_t n, const double* pos, const int32_t*
         require(p->sampling_strategy == GMG_SAMPLING_FASTDISK, "only Sampling.FASTDISK is implemented (the others are paper ablations)");
         require(!p->sig06 && !p->ablation, "the SIG06 and ablation hierarchies are out of scope");
         require(p->weighting >= 0 && p->weighting <= 2, "unknown weighting scheme");
-        require(p->smoother == GMG_SMOOTHER_JACOBI, "unknown smoother");
+        require(p->smoother == GMG_SMOOTHER_JACOBI || p->smoother == GMG_SMOOTHER_CHEBYSHEV, "unknown smoother");
+        require(p->cheb_alpha > 1.0, "cheb_alpha must be > 1");
+        require(p->pre_iters >= 0 && p->pre_iters <= 16 && p->post_iters >= 0 && p->post_iters <= 16, "sweep counts must be 0..16");
         require(p->dtype == GMG_DTYPE_F64 || p->dtype == GMG_DTYPE_F32, "unknown dtype");
         std::unique_ptr<gmg_solver> h(new gmg_solver());
         SolverState& s = h->s;
@@ -140,13 +143,19 @@ int gmg_set_option(gmg_handle h, const char* key, double value) {
         else if (k == "pre_iters") s.params.pre_iters = (int)value, cycle = true;
         else if (k == "post_iters") s.params.post_iters = (int)value, cycle = true;
         else if (k == "omega") s.params.omega = value, cycle = true;
+        else if (k == "smoother") s.params.smoother = (int)value, cycle = true;
+        else if (k == "cheb_alpha") s.params.cheb_alpha = value, cycle = true;
+        else if (k == "lanes") s.staged_lanes = (int)value, hierarchy = true;
         else if (k == "cycle_type") s.params.cycle_type = (int)value;
         else if (k == "use_graph") s.use_graph = value != 0.0;
         else if (k == "loop_mode") s.loop_mode = (int)value;
         else if (k == "profile") s.profile = value != 0.0;
         else if (k == "kernel_path") s.kernel_path = (int)value, hierarchy = true;
         else throw std::invalid_argument("unknown option: " + k);
-        require(s.params.pre_iters >= 0 && s.params.post_iters >= 0, "sweep counts must be >= 0");
+        require(s.params.pre_iters >= 0 && s.params.post_iters >= 0 && s.params.pre_iters <= 16 && s.params.post_iters <= 16, "sweep counts must be 0..16");
+        require(s.params.smoother == GMG_SMOOTHER_JACOBI || s.params.smoother == GMG_SMOOTHER_CHEBYSHEV, "unknown smoother");
+        require(s.params.cheb_alpha > 1.0, "cheb_alpha must be > 1");
+        require(s.staged_lanes == 0 || s.staged_lanes == 1 || s.staged_lanes == 2 || s.staged_lanes == 4 || s.staged_lanes == 8, "lanes must be 0, 1, 2, 4 or 8");
         if (s.engine && hierarchy) s.engine->invalidate_hierarchy();
         if (s.engine && cycle) s.engine->invalidate_cycle();
     });
@@ -164,6 +173,9 @@ int gmg_get_option(gmg_handle h, const char* key, double* value) {
         else if (k == "pre_iters") *value = s.params.pre_iters;
         else if (k == "post_iters") *value = s.params.post_iters;
         else if (k == "omega") *value = s.params.omega;
+        else if (k == "smoother") *value = s.params.smoother;
+        else if (k == "cheb_alpha") *value = s.params.cheb_alpha;
+        else if (k == "lanes") *value = s.staged_lanes;
         else if (k == "cycle_type") *value = s.params.cycle_type;
         else if (k == "use_graph") *value = s.use_graph;
         else if (k == "loop_mode") *value = s.loop_mode;
@@ -351,6 +363,15 @@ int gmg_level_op(gmg_handle h, int32_t kind, int32_t level, const double* a, con
         require(out != nullptr, "null argument");
         require(h->s.engine != nullptr, "gmg_level_op needs a staged system (gmg_stage_system)");
         h->s.engine->level_op(kind, level, a, b, out, sweeps);
+    });
+}
+
+int gmg_get_smoother_weights(gmg_handle h, int32_t level, double* rho, double* pre, double* post) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(rho && pre && post, "null argument");
+        require(h->s.engine != nullptr, "no system staged on the device");
+        h->s.engine->smoother_weights(level, rho, pre, post);
     });
 }
 

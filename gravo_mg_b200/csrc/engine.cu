@@ -52,7 +52,7 @@ struct DevMat {
         launch_expand_rows(rows, indptr.ptr, rowidx.ptr, s);
     }
     // Choose the kernel path and build the row tiles for the staged one.
-    void make_plan(const std::vector<int>& indptr_h, int prefer_path, cudaStream_t s) {
+    void make_plan(const std::vector<int>& indptr_h, int prefer_path, int staged_lanes, cudaStream_t s) {
         const double avg = rows ? (double)nnz / rows : 0.0;
         int lanes = 1;
         while (lanes < 32 && lanes < avg) lanes *= 2;
@@ -60,14 +60,19 @@ struct DevMat {
         plan.lanes = lanes;
         plan.path = 1;
         if (prefer_path == 0 && rows > 0) {
-            // stage budget: 3 stages, two resident CTAs per SM
-            const size_t per_stage = (staged_smem_limit() / 2 - 256) / kStagedStages;
+            // threads per row of the staged kernel: enough rows per tile to keep the CTA busy, few
+            // enough entries per tile that many CTAs fit one SM's shared memory
+            int sl = staged_lanes;
+            if (sl == 0) sl = avg <= 5.0 ? 1 : avg <= 12.0 ? 2 : avg <= 28.0 ? 4 : 8;
+            // stage budget: kStagedStages stages, at least two resident CTAs per SM
+            const size_t per_stage = (staged_smem_limit() / 2 - 1280) / kStagedStages;
             const int cap = (int)(per_stage / (sizeof(T) + sizeof(int))) & ~3;
             int worst = 0;
-            std::vector<int> t = plan_row_tiles(indptr_h, kStagedThreads, cap, &worst);
+            std::vector<int> t = plan_row_tiles(indptr_h, kStagedThreads / sl, cap, &worst);
             if (worst <= cap) {
                 tiles.upload(t, s);
                 plan.path = 0;
+                plan.staged_lanes = sl;
                 plan.n_tiles = (int)t.size() - 1;
                 plan.stage_elems = std::max((worst + 3) & ~3, 4);
                 plan.tile_rows = tiles.ptr;
@@ -98,6 +103,9 @@ public:
         ctl_.ensure(2);
         GMG_CUDA(cudaMemsetAsync(ctl_.ptr, 0, 2 * sizeof(CycleControl), stream_));
         partials_.ensure(kNormChunkStride * kMaxNormChunks);
+        rho_.ensure(kMaxLevels);
+        weights_.ensure((size_t)kMaxLevels * 2 * kMaxSweeps);
+        weights64_.ensure((size_t)kMaxLevels * 2 * kMaxSweeps);
         GMG_CUDA(cudaMallocHost((void**)&ctl_host_, sizeof(CycleControl)));
         std::vector<double> minv(st->mass_diag.size());
         for (size_t i = 0; i < minv.size(); ++i) minv[i] = st->mass_diag[i] != 0.0 ? 1.0 / st->mass_diag[i] : 0.0;  // igl::invert_diag
@@ -122,6 +130,7 @@ public:
     }
     void invalidate_cycle() override {
         cycle_dirty_ = true;
+        numeric_ready_ = false;  // the smoother dampings are part of the numeric setup
     }
 
     // ------------------------------------------------------------------ staging
@@ -277,9 +286,12 @@ public:
     // the values of A staged on the device. Returns the number of kernel launches.
     int64_t setup_numeric(cudaEvent_t after_reduction) {
         const int L = n_levels_;
+        const gmg_params& p = st_->params;
         int64_t launches = 0;
+        GMG_CUDA(cudaMemsetAsync(rho_.ptr, 0, kMaxLevels * sizeof(double), stream_));
         if (L > 0) {
-            launch_extract_dinv<T>(lv_[0].n, lv_[0].A.indptr.ptr, lv_[0].A.indices.ptr, lv_[0].A.v64.ptr, lv_[0].dinv.ptr, ctl_.ptr, stream_);
+            launch_extract_dinv<T>(lv_[0].n, lv_[0].A.indptr.ptr, lv_[0].A.indices.ptr, lv_[0].A.v64.ptr, lv_[0].dinv.ptr,
+                                   rho_.ptr, ctl_.ptr, stream_);
             ++launches;
         }
         lv_[0].A.refresh_cast(stream_);
@@ -293,16 +305,34 @@ public:
                                   f.R.v64.ptr, f.AP.indptr.ptr, f.AP.indices.ptr, f.AP.v64.ptr, stream_);
             launches += 2;
             if (k + 1 < L) {
-                launch_extract_dinv<T>(c.n, c.A.indptr.ptr, c.A.indices.ptr, c.A.v64.ptr, c.dinv.ptr, ctl_.ptr, stream_);
+                launch_extract_dinv<T>(c.n, c.A.indptr.ptr, c.A.indices.ptr, c.A.v64.ptr, c.dinv.ptr, rho_.ptr + k + 1, ctl_.ptr,
+                                       stream_);
                 c.A.refresh_cast(stream_);
                 launches += sizeof(T) == 4 ? 2 : 1;
             }
+        }
+        if (L > 0) {
+            launch_smoother_weights<T>(rho_.ptr, L, p.pre_iters, p.post_iters, p.smoother, p.omega, p.cheb_alpha, weights_.ptr,
+                                       weights64_.ptr, stream_);
+            ++launches;
         }
         if (after_reduction) GMG_CUDA(cudaEventRecord(after_reduction, stream_));
         coarse_.factor(lv_[L].A.indptr.ptr, lv_[L].A.indices.ptr, lv_[L].A.v64.ptr, ctl_.ptr, stream_);
         launches += coarse_.launches_per_factor();
         numeric_ready_ = true;
         return launches;
+    }
+
+    void smoother_weights(int level, double* rho, double* pre, double* post) override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        if (!numeric_ready_) throw std::logic_error("smoother weights exist after a solve or a level_op");
+        if (level < 0 || level >= n_levels_) throw std::invalid_argument("level has no smoother");
+        double w[2 * kMaxSweeps];
+        GMG_CUDA(cudaMemcpyAsync(rho, rho_.ptr + level, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        GMG_CUDA(cudaMemcpyAsync(w, weights64_.ptr + (size_t)level * 2 * kMaxSweeps, sizeof w, cudaMemcpyDeviceToHost, stream_));
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+        for (int j = 0; j < st_->params.pre_iters; ++j) pre[j] = w[j];
+        for (int j = 0; j < st_->params.post_iters; ++j) post[j] = w[kMaxSweeps + j];
     }
 
     void check_setup_errors() {
@@ -359,8 +389,10 @@ public:
                 T* cur = f.x.ptr;
                 T* alt = f.t.ptr;
                 op.kind = OP_JACOBI, op.epi = EPI_JACOBI, op.plan = &f.A.plan, op.args = base_args(f.A);
+                if (st_->params.pre_iters < 1) throw std::invalid_argument("level_op jacobi uses the pre-smoothing dampings: pre_iters must be >= 1");
                 for (int i = 0; i < sweeps; ++i) {
                     op.args.x = cur, op.args.b = f.b.ptr, op.args.dinv = f.dinv.ptr, op.args.out = alt;
+                    op.args.omega_ptr = weight_ptr(level, false, i % st_->params.pre_iters);
                     run_op(op, stream_, 0);
                     std::swap(cur, alt);
                 }
@@ -475,12 +507,12 @@ private:
             lv_[k].P.upload_pattern(u, stream_);
             lv_[k].P.upload_values(u.data.data(), stream_);
             lv_[k].P.refresh_cast(stream_);
-            lv_[k].P.make_plan(u.indptr, st_->kernel_path, stream_);
+            lv_[k].P.make_plan(u.indptr, st_->kernel_path, st_->staged_lanes, stream_);
             HostCsr r = transpose(u);
             lv_[k].R.upload_pattern(r, stream_);
             lv_[k].R.upload_values(r.data.data(), stream_);
             lv_[k].R.refresh_cast(stream_);
-            lv_[k].R.make_plan(r.indptr, st_->kernel_path, stream_);
+            lv_[k].R.make_plan(r.indptr, st_->kernel_path, st_->staged_lanes, stream_);
             r_host_.push_back(std::move(r));
         }
         GMG_CUDA(cudaStreamSynchronize(stream_));
@@ -499,7 +531,7 @@ private:
         cur.indptr = a_indptr_h_;
         cur.indices = a_indices_h_;
         lv_[0].A.upload_pattern(cur, stream_);
-        lv_[0].A.make_plan(cur.indptr, st_->kernel_path, stream_);
+        lv_[0].A.make_plan(cur.indptr, st_->kernel_path, st_->staged_lanes, stream_);
         for (int k = 0; k < n_levels_; ++k) {
             HostCsr ap = spgemm_symbolic(cur, st_->hier.U[k]);
             HostCsr ac = spgemm_symbolic(r_host_[k], ap);
@@ -507,7 +539,7 @@ private:
             lv_[k].AP.make_rowidx(stream_);
             lv_[k + 1].A.upload_pattern(ac, stream_);
             lv_[k + 1].A.make_rowidx(stream_);
-            lv_[k + 1].A.make_plan(ac.indptr, st_->kernel_path, stream_);
+            lv_[k + 1].A.make_plan(ac.indptr, st_->kernel_path, st_->staged_lanes, stream_);
             cur = std::move(ac);
         }
         for (int k = 0; k <= n_levels_; ++k) lv_[k].dinv.ensure(std::max(lv_[k].n, 1));
@@ -553,12 +585,18 @@ private:
         return a;
     }
 
-    void push_sweeps(int k, int count, T*& cur, T*& alt) {
-        for (int i = 0; i < count; ++i) {
+    const T* weight_ptr(int level, bool post, int sweep) const {
+        return weights_.ptr + ((size_t)level * 2 + (post ? 1 : 0)) * kMaxSweeps + sweep;
+    }
+
+    // Sweeps [first, last) of the pre- or post-smoothing sequence of level k.
+    void push_sweeps(int k, bool post, int first, int last, T*& cur, T*& alt) {
+        for (int i = first; i < last; ++i) {
             Op op;
             op.kind = OP_JACOBI, op.level = k, op.epi = EPI_JACOBI, op.plan = &lv_[k].A.plan;
             op.args = base_args(lv_[k].A);
             op.args.x = cur, op.args.b = lv_[k].b.ptr, op.args.dinv = lv_[k].dinv.ptr, op.args.out = alt;
+            op.args.omega_ptr = weight_ptr(k, post, i);
             ops_.push_back(op);
             std::swap(cur, alt);
         }
@@ -571,7 +609,7 @@ private:
         const int L = n_levels_;
         Level& f = lv_[k];
         Level& c = lv_[k + 1];
-        push_sweeps(k, p.pre_iters - pre_done, cur, alt);
+        push_sweeps(k, false, pre_done, p.pre_iters, cur, alt);
         {   // res = b - A x
             Op op;
             op.kind = OP_RESIDUAL, op.level = k, op.epi = EPI_RESIDUAL, op.plan = &f.A.plan;
@@ -588,7 +626,7 @@ private:
             op.kind = OP_RESTRICT, op.level = k, op.epi = EPI_SPMV, op.plan = &f.R.plan;
             op.args = base_args(f.R);
             op.args.x = f.r.ptr, op.args.out = c.b.ptr;
-            if (next_pre_done) op.args.out2 = c.x.ptr, op.args.dinv = c.dinv.ptr;
+            if (next_pre_done) op.args.out2 = c.x.ptr, op.args.dinv = c.dinv.ptr, op.args.omega_ptr = weight_ptr(k + 1, false, 0);
             ops_.push_back(op);
         }
         T* ccur = c.x.ptr;
@@ -616,7 +654,7 @@ private:
             ops_.push_back(op);
             if (flip) std::swap(cur, alt);
         }
-        push_sweeps(k, p.post_iters, cur, alt);
+        push_sweeps(k, true, 0, p.post_iters, cur, alt);
     }
 
     void build_cycle() {
@@ -811,6 +849,8 @@ private:
     DeviceBuffer<CycleControl> ctl_;
     CycleControl* ctl_host_ = nullptr;
     DeviceBuffer<double> hist_res_, hist_ms_, partials_, mass_, minv_, rhs64_, x64_, coarse_b64_, coarse_x64_, io64_;
+    DeviceBuffer<double> rho_, weights64_;
+    DeviceBuffer<T> weights_;
     DeviceBuffer<int> q_indptr_, q_indices_;
     DeviceBuffer<double> q_vals_, q_b_, q_x_;
     std::vector<int> a_indptr_h_, a_indices_h_;

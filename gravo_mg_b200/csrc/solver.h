@@ -24,6 +24,7 @@ public:
     virtual double residual(int64_t n, const int* indptr, const int* indices, const double* data, const double* rhs,
                             const double* x, int K, int type) = 0;
     virtual void level_op(int kind, int level, const double* a, const double* b, double* out, int sweeps) = 0;
+    virtual void smoother_weights(int level, double* rho, double* pre, double* post) = 0;
     virtual void get_level_matrix(int level, int* indptr, int* indices, double* data) = 0;
     virtual void invalidate_hierarchy() = 0;
     virtual void invalidate_cycle() = 0;
@@ -40,6 +41,7 @@ struct SolverState {
     bool use_graph = true;
     int loop_mode = 0;               // 0 host loop (one sync per cycle), 1 device while-graph
     int kernel_path = 0;             // 0 staged (TMA) where it fits, 1 direct everywhere
+    int staged_lanes = 0;            // staged kernels: threads per row; 0 = from the mean row length
     bool profile = false;
     std::map<std::string, double> solver_timing;           // reference solverTiming keys
     std::vector<std::pair<double, double>> convergence;    // (elapsed ms, residue) per cycle

@@ -73,19 +73,62 @@ __global__ void norm_finalize_kernel(const double* __restrict__ partials, NormCh
     }
 }
 
+// dinv_i = 1 / A_ii, and rho = max_i sum_j |A_ij| / A_ii (Gershgorin bound of the spectral radius
+// of D^-1 A, the upper end of the band the Chebyshev-weighted Jacobi sweeps damp).
 template <typename T>
-__global__ void extract_dinv_kernel(int n, const int* __restrict__ rowptr, const int* __restrict__ colidx,
-                                    const double* __restrict__ vals, T* __restrict__ dinv, CycleControl* ctl) {
+__global__ void __launch_bounds__(256) extract_dinv_kernel(int n, const int* __restrict__ rowptr,
+                                                          const int* __restrict__ colidx,
+                                                          const double* __restrict__ vals, T* __restrict__ dinv,
+                                                          double* __restrict__ rho, CycleControl* ctl) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double d = 0.0;
-    for (int p = rowptr[i]; p < rowptr[i + 1]; ++p)
-        if (colidx[p] == i) d += vals[p];
-    if (!(d > 0.0) || d > 1.7976931348623157e308) {
-        atomicOr(&ctl->error, 1);
-        dinv[i] = T(0);
-    } else {
-        dinv[i] = (T)(1.0 / d);
+    double bound = 0.0;
+    if (i < n) {
+        double d = 0.0, absum = 0.0;
+        for (int p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+            const double v = vals[p];
+            if (colidx[p] == i) d += v;
+            absum += fabs(v);
+        }
+        if (!(d > 0.0) || d > 1.7976931348623157e308) {
+            atomicOr(&ctl->error, 1);
+            dinv[i] = T(0);
+        } else {
+            const double inv = 1.0 / d;
+            dinv[i] = (T)inv;
+            bound = absum * inv;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bound = fmax(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+    __shared__ double sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = bound;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) bound = fmax(bound, sh[w]);
+        // non-negative doubles order like their bit patterns
+        atomicMax(reinterpret_cast<unsigned long long*>(rho), (unsigned long long)__double_as_longlong(bound));
+    }
+}
+
+// Per-level, per-sweep Jacobi dampings. Layout: weights[(level * 2 + post) * kMaxSweeps + sweep].
+template <typename T>
+__global__ void smoother_weights_kernel(const double* __restrict__ rho, int n_levels, int pre, int post, int smoother,
+                                        double omega, double alpha, T* __restrict__ weights, double* __restrict__ weights64) {
+    const int level = threadIdx.x;
+    if (level >= n_levels) return;
+    const double hi = rho[level], lo = hi / alpha;
+    for (int side = 0; side < 2; ++side) {
+        const int deg = side ? post : pre;
+        for (int j = 0; j < deg; ++j) {
+            double w = omega;
+            if (smoother == 1) {
+                const int jj = side ? deg - 1 - j : j;  // post-smoothing runs the roots in reverse
+                const double root = 0.5 * (hi + lo) + 0.5 * (hi - lo) * cospi((2.0 * jj + 1.0) / (2.0 * deg));
+                w = 1.0 / root;
+            }
+            weights[(level * 2 + side) * kMaxSweeps + j] = (T)w;
+            weights64[(level * 2 + side) * kMaxSweeps + j] = w;
+        }
     }
 }
 
@@ -190,6 +233,17 @@ int resident_blocks(const void* kernel, int threads, size_t smem) {
     return nb;
 }
 
+template <typename T, int K, int EPI, int LANES>
+int launch_staged(SpmvArgs<T>& a, const SpmvPlan& plan, cudaStream_t stream) {
+    const size_t smem = staged_smem_bytes(plan.stage_elems, sizeof(T));
+    auto kernel = spmv_staged_kernel<T, K, EPI, LANES>;
+    const int per_sm = resident_blocks((const void*)kernel, kStagedThreads, smem);
+    int grid = std::min(std::max(plan.n_tiles, 1), per_sm * num_sms());
+    if (EPI == EPI_NORM) grid = std::min(grid, kMaxNormBlocks);
+    if (!g_dry_run) kernel<<<grid, kStagedThreads, smem, stream>>>(a);
+    return grid;
+}
+
 template <typename T, int K, int EPI>
 int launch_one(SpmvArgs<T>& a, const SpmvPlan& plan, cudaStream_t stream) {
     int grid = 0;
@@ -197,12 +251,12 @@ int launch_one(SpmvArgs<T>& a, const SpmvPlan& plan, cudaStream_t stream) {
         a.tile_rows = plan.tile_rows;
         a.n_tiles = plan.n_tiles;
         a.stage_elems = plan.stage_elems;
-        const size_t smem = staged_smem_bytes(plan.stage_elems, sizeof(T));
-        auto kernel = spmv_staged_kernel<T, K, EPI>;
-        const int per_sm = resident_blocks((const void*)kernel, kStagedThreads, smem);
-        grid = std::min(std::max(plan.n_tiles, 1), per_sm * num_sms());
-        if (EPI == EPI_NORM) grid = std::min(grid, kMaxNormBlocks);
-        if (!g_dry_run) kernel<<<grid, kStagedThreads, smem, stream>>>(a);
+        switch (plan.staged_lanes) {
+            case 1: grid = launch_staged<T, K, EPI, 1>(a, plan, stream); break;
+            case 2: grid = launch_staged<T, K, EPI, 2>(a, plan, stream); break;
+            case 4: grid = launch_staged<T, K, EPI, 4>(a, plan, stream); break;
+            default: grid = launch_staged<T, K, EPI, 8>(a, plan, stream); break;
+        }
     } else {
         const int rows_per_block = kDirectThreads / plan.lanes;
         const int64_t want = ((int64_t)a.n_rows + rows_per_block - 1) / rows_per_block;
@@ -264,14 +318,24 @@ void launch_cycle_begin(CycleControl* ctl, int max_iter, int criterion, double t
 }
 
 template <typename T>
-void launch_extract_dinv(int n, const int* rowptr, const int* colidx, const double* vals, T* dinv, CycleControl* ctl,
-                         cudaStream_t stream) {
+void launch_extract_dinv(int n, const int* rowptr, const int* colidx, const double* vals, T* dinv, double* rho,
+                         CycleControl* ctl, cudaStream_t stream) {
     if (n <= 0) return;
-    extract_dinv_kernel<T><<<(n + 255) / 256, 256, 0, stream>>>(n, rowptr, colidx, vals, dinv, ctl);
+    extract_dinv_kernel<T><<<(n + 255) / 256, 256, 0, stream>>>(n, rowptr, colidx, vals, dinv, rho, ctl);
     GMG_CUDA(cudaGetLastError());
 }
-template void launch_extract_dinv<double>(int, const int*, const int*, const double*, double*, CycleControl*, cudaStream_t);
-template void launch_extract_dinv<float>(int, const int*, const int*, const double*, float*, CycleControl*, cudaStream_t);
+template void launch_extract_dinv<double>(int, const int*, const int*, const double*, double*, double*, CycleControl*, cudaStream_t);
+template void launch_extract_dinv<float>(int, const int*, const int*, const double*, float*, double*, CycleControl*, cudaStream_t);
+
+template <typename T>
+void launch_smoother_weights(const double* rho, int n_levels, int pre, int post, int smoother, double omega, double alpha,
+                             T* weights, double* weights64, cudaStream_t stream) {
+    if (n_levels <= 0) return;
+    smoother_weights_kernel<T><<<1, 32, 0, stream>>>(rho, n_levels, pre, post, smoother, omega, alpha, weights, weights64);
+    GMG_CUDA(cudaGetLastError());
+}
+template void launch_smoother_weights<double>(const double*, int, int, int, int, double, double, double*, double*, cudaStream_t);
+template void launch_smoother_weights<float>(const double*, int, int, int, int, double, double, float*, double*, cudaStream_t);
 
 static int stream_grid(size_t n) { return (int)std::min<size_t>((n + 255) / 256, (size_t)148 * 16); }
 

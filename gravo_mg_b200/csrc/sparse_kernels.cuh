@@ -13,10 +13,12 @@
 // Two data paths:
 //   staged  persistent CTAs walk row tiles; the tile's contiguous (colidx, vals) slab is
 //           brought into shared memory by the TMA engine (cp.async.bulk + mbarrier, a
-//           STAGES-deep ring), then one thread owns one row and reads its entries from
-//           shared memory, so global loads/stores of b, x, dinv, out are fully coalesced and
-//           the products are summed in CSR order (bit-identical to a sequential CPU loop;
-//           the library is compiled with -fmad=false for that reason).
+//           STAGES-deep ring), then LANES threads own one row and read its entries from
+//           shared memory (consecutive lanes, consecutive entries: conflict free), gather x
+//           through L1/L2 and combine with a shuffle butterfly. With LANES = 1 the products
+//           are summed in CSR order, bit-identical to a sequential CPU loop (the library is
+//           compiled with -fmad=false for that reason); LANES > 1 trades that for more rows
+//           in flight per byte of shared memory (short tiles, many resident CTAs).
 //   direct  LANES threads per row straight from global memory with a shuffle reduction;
 //           used when a row does not fit a stage and as an independent cross-check.
 #pragma once
@@ -54,6 +56,7 @@ struct SpmvArgs {
     T* out = nullptr;
     T* out2 = nullptr;
     T omega = T(0);
+    const T* omega_ptr = nullptr;      // device-resident damping of this sweep (overrides omega)
     double* partials = nullptr;        // NORM: [gridDim.x][2*K]
     const int* tile_rows = nullptr;    // staged: n_tiles + 1 row offsets
     int n_tiles = 0;
@@ -84,41 +87,71 @@ __device__ __forceinline__ void block_sum_store(double (&v)[NV], double* out) {
     }
 }
 
+// Own-row operands of the epilogue. They do not depend on the row product, so the staged kernel
+// loads them before it waits for the tile's slab (their latency hides behind the bulk copy).
+template <typename T, int K>
+struct RowOperands {
+    T b[K];
+    T xo[K];
+    T scale;     // omega * dinv
+    double w;    // NORM weight
+};
+
 template <typename T, int K, int EPI>
-__device__ __forceinline__ void row_epilogue(const SpmvArgs<T>& a, int row, const T (&acc)[K], double (&nrm)[2 * K]) {
+__device__ __forceinline__ void load_row_operands(const SpmvArgs<T>& a, int row, RowOperands<T, K>& r) {
+    const size_t o = (size_t)row * a.ld;
+    if (EPI == EPI_JACOBI || (EPI == EPI_SPMV && a.out2)) {
+        const T om = a.omega_ptr ? *a.omega_ptr : a.omega;
+        r.scale = om * a.dinv[row];
+    }
+    if (EPI == EPI_JACOBI || EPI == EPI_RESIDUAL || EPI == EPI_NORM) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) r.b[k] = a.b[o + k];
+    }
+    if (EPI == EPI_JACOBI) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) r.xo[k] = a.x[o + k];
+    }
+    if (EPI == EPI_ADD) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) r.xo[k] = a.xin[o + k];
+    }
+    if (EPI == EPI_NORM) r.w = a.weight ? a.weight[row] : 1.0;
+}
+
+template <typename T, int K, int EPI>
+__device__ __forceinline__ void row_epilogue(const SpmvArgs<T>& a, int row, const T (&acc)[K], const RowOperands<T, K>& r,
+                                             double (&nrm)[2 * K]) {
     const size_t o = (size_t)row * a.ld;
     if (EPI == EPI_SPMV) {
 #pragma unroll
         for (int k = 0; k < K; ++k) a.out[o + k] = acc[k];
         if (a.out2) {
-            const T s = a.omega * a.dinv[row];
 #pragma unroll
-            for (int k = 0; k < K; ++k) a.out2[o + k] = s * acc[k];
+            for (int k = 0; k < K; ++k) a.out2[o + k] = r.scale * acc[k];
         }
     } else if (EPI == EPI_JACOBI) {
-        const T s = a.omega * a.dinv[row];
 #pragma unroll
-        for (int k = 0; k < K; ++k) a.out[o + k] = a.x[o + k] + s * (a.b[o + k] - acc[k]);
+        for (int k = 0; k < K; ++k) a.out[o + k] = r.xo[k] + r.scale * (r.b[k] - acc[k]);
     } else if (EPI == EPI_RESIDUAL) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) a.out[o + k] = a.b[o + k] - acc[k];
+        for (int k = 0; k < K; ++k) a.out[o + k] = r.b[k] - acc[k];
     } else if (EPI == EPI_ADD) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) a.out[o + k] = a.xin[o + k] + acc[k];
+        for (int k = 0; k < K; ++k) a.out[o + k] = r.xo[k] + acc[k];
     } else {  // EPI_NORM
-        const double w = a.weight ? a.weight[row] : 1.0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const double bk = (double)a.b[o + k];
-            const double r = (double)acc[k] - bk;
-            nrm[2 * k] += w * r * r;
-            nrm[2 * k + 1] += w * bk * bk;
+            const double bk = (double)r.b[k];
+            const double d = (double)acc[k] - bk;
+            nrm[2 * k] += r.w * d * d;
+            nrm[2 * k + 1] += r.w * bk * bk;
         }
     }
 }
 
 // ---------------------------------------------------------------------------- staged path
-template <typename T, int K, int EPI>
+template <typename T, int K, int EPI, int LANES>
 __global__ void __launch_bounds__(kStagedThreads) spmv_staged_kernel(const SpmvArgs<T> a) {
     constexpr int TPB = kStagedThreads;
     constexpr int STAGES = kStagedStages;
@@ -130,6 +163,7 @@ __global__ void __launch_bounds__(kStagedThreads) spmv_staged_kernel(const SpmvA
     unsigned char* stage0 = smem_raw + 128;
 
     const int tid = threadIdx.x;
+    const int lane = tid % LANES;
     const int n_my = (int)blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (tid == 0) {
@@ -166,32 +200,39 @@ __global__ void __launch_bounds__(kStagedThreads) spmv_staged_kernel(const SpmvA
         const int r0 = a.tile_rows[tile];
         const int r1 = a.tile_rows[tile + 1];
         const int base = a.rowptr[r0] & ~3;
-        const int row = r0 + tid;
+        const int row = r0 + tid / LANES;
         const bool active = row < r1;
         int ps = 0, pe = 0;
+        RowOperands<T, K> ops;
         if (active) {
             ps = a.rowptr[row] - base;
             pe = a.rowptr[row + 1] - base;
+            if (lane == 0) load_row_operands<T, K, EPI>(a, row, ops);
         }
         const T* sv = reinterpret_cast<const T*>(stage0 + s * stage_bytes);
         const int* sc = reinterpret_cast<const int*>(stage0 + s * stage_bytes + (size_t)a.stage_elems * sizeof(T));
 
         mbar_wait(&bars[s], (uint32_t)((it / STAGES) & 1));
 
-        if (active) {
-            T acc[K];
+        T acc[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] = T(0);
+        for (int k = 0; k < K; ++k) acc[k] = T(0);
 #pragma unroll 4
-            for (int p = ps; p < pe; ++p) {
-                const int c = sc[p];
-                const T v = sv[p];
-                const T* xp = a.x + (size_t)c * a.ld;
+        for (int p = ps + lane; p < pe; p += LANES) {
+            const int c = sc[p];
+            const T v = sv[p];
+            const T* xp = a.x + (size_t)c * a.ld;
 #pragma unroll
-                for (int k = 0; k < K; ++k) acc[k] += v * __ldg(xp + k);
-            }
-            row_epilogue<T, K, EPI>(a, row, acc, nrm);
+            for (int k = 0; k < K; ++k) acc[k] += v * __ldg(xp + k);
         }
+        if (LANES > 1) {
+#pragma unroll
+            for (int o = LANES / 2; o > 0; o >>= 1) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+            }
+        }
+        if (active && lane == 0) row_epilogue<T, K, EPI>(a, row, acc, ops, nrm);
         __syncthreads();  // everyone is done reading stage s before it is refilled
         if (tid == 0 && it + STAGES < n_my) issue(it + STAGES);
     }
@@ -231,7 +272,11 @@ __global__ void __launch_bounds__(kDirectThreads) spmv_direct_kernel(const SpmvA
 #pragma unroll
             for (int k = 0; k < K; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
         }
-        if (active && lane == 0) row_epilogue<T, K, EPI>(a, row, acc, nrm);
+        if (active && lane == 0) {
+            RowOperands<T, K> ops;
+            load_row_operands<T, K, EPI>(a, row, ops);
+            row_epilogue<T, K, EPI>(a, row, acc, ops, nrm);
+        }
     }
     if (EPI == EPI_NORM) block_sum_store<2 * K, TPB>(nrm, a.partials + (size_t)blockIdx.x * 2 * K);
 }

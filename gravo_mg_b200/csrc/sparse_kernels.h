@@ -8,6 +8,7 @@ namespace gmg {
 struct SpmvPlan {
     int path = 1;            // 0 staged (TMA), 1 direct
     int lanes = 8;           // direct: threads per row (1, 2, 4, 8, 16, 32)
+    int staged_lanes = 1;    // staged: threads per row (1, 2, 4, 8); 1 sums in CSR order
     int n_tiles = 0;         // staged
     int stage_elems = 0;     // staged: entries per stage (multiple of 4)
     const int* tile_rows = nullptr;  // device array n_tiles + 1
@@ -43,9 +44,16 @@ void launch_norm_finalize(const double* partials, const NormChunks& chunks, Cycl
                           double* hist_ms, int record, unsigned long long cond_handle, cudaStream_t stream);
 void launch_cycle_begin(CycleControl* ctl, int max_iter, int criterion, double tol, int n_cols, cudaStream_t stream);
 
+constexpr int kMaxSweeps = 16;        // pre / post sweeps per level the weight table holds
+
+// dinv = 1 / diag(A) and *rho = max(*rho, Gershgorin bound of D^-1 A) (zero *rho first).
 template <typename T>
-void launch_extract_dinv(int n, const int* rowptr, const int* colidx, const double* vals, T* dinv, CycleControl* ctl,
-                         cudaStream_t stream);
+void launch_extract_dinv(int n, const int* rowptr, const int* colidx, const double* vals, T* dinv, double* rho,
+                         CycleControl* ctl, cudaStream_t stream);
+// Jacobi dampings per level and sweep from rho[level]: weights[(level * 2 + post) * kMaxSweeps + sweep].
+template <typename T>
+void launch_smoother_weights(const double* rho, int n_levels, int pre, int post, int smoother, double omega, double alpha,
+                             T* weights, double* weights64, cudaStream_t stream);
 void launch_cast_f64_f32(const double* src, float* dst, size_t n, cudaStream_t stream);
 void launch_cast_f32_f64(const float* src, double* dst, size_t n, cudaStream_t stream);
 void launch_expand_rows(int n_rows, const int* rowptr, int* rowidx, cudaStream_t stream);

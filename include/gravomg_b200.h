@@ -28,7 +28,7 @@ typedef struct gmg_solver* gmg_handle;
 /* Enumerations of the reference (gravomg/include/gravomg/multigrid_solver.h:35-52). */
 enum { GMG_SAMPLING_FASTDISK = 0, GMG_SAMPLING_POISSONDISK = 1, GMG_SAMPLING_FPS = 2, GMG_SAMPLING_RANDOM = 3, GMG_SAMPLING_MIS = 4 };
 enum { GMG_WEIGHTING_BARYCENTRIC = 0, GMG_WEIGHTING_UNIFORM = 1, GMG_WEIGHTING_INVDIST = 2 };
-enum { GMG_SMOOTHER_JACOBI = 0 };
+enum { GMG_SMOOTHER_JACOBI = 0, GMG_SMOOTHER_CHEBYSHEV = 1 };
 enum { GMG_DTYPE_F64 = 0, GMG_DTYPE_F32 = 1 };
 
 /* Constructor arguments of the reference binding (core.cpp:20-58; Python defaults core.py:8-13)
@@ -53,11 +53,15 @@ typedef struct gmg_params {
     int32_t ablation_num_points;
     int32_t ablation_random;
     /* ---- additions ---- */
-    int32_t smoother;           /* GMG_SMOOTHER_JACOBI: damped Jacobi x += omega D^-1 (b - A x) */
-    double omega;               /* damping, default 2/3 */
+    int32_t smoother;           /* GMG_SMOOTHER_CHEBYSHEV (default): Jacobi sweeps x += w_j D^-1 (b - A x) whose
+                                   dampings w_j are the inverse roots of the Chebyshev polynomial of degree
+                                   pre_iters (post_iters) on [rho/cheb_alpha, rho], rho = Gershgorin bound of
+                                   D^-1 A per level; GMG_SMOOTHER_JACOBI: every sweep uses omega */
+    double omega;               /* fixed damping of GMG_SMOOTHER_JACOBI, default 2/3 */
     int32_t dtype;              /* GMG_DTYPE_F64 (default) | GMG_DTYPE_F32 smoother levels */
     int32_t device;             /* CUDA device ordinal, default 0 */
     int32_t build_hierarchy;    /* 1: build U at create (reference behaviour); 0: caller injects U */
+    double cheb_alpha;          /* width of the smoothed band, default 10 */
 } gmg_params;
 
 /* Fill *p with the reference's Python defaults. */
@@ -75,8 +79,10 @@ const char* gmg_last_error(gmg_handle h);
 /* Change a solve-time setting after construction (the reference exposes them as public
  * members: accuracy, stoppingCriteria, preIters, postIters, maxIter; multigrid_solver.h:131-144).
  * Keys: "tolerance", "stopping_criteria", "pre_iters", "post_iters", "max_iter", "omega",
- * and implementation knobs "use_graph" (0/1), "loop_mode" (0 host loop, 1 device while-graph),
- * "kernel_path" (0 staged TMA, 1 direct), "profile" (0/1 per-kernel event timing). */
+ * "smoother", "cheb_alpha", and implementation knobs "use_graph" (0/1), "loop_mode" (0 host loop,
+ * 1 device while-graph), "kernel_path" (0 staged TMA, 1 direct), "lanes" (staged kernels: threads
+ * per row, 0 = chosen from the row length, 1 = one thread per row, sums in CSR order),
+ * "profile" (0/1 per-kernel event timing). */
 int gmg_set_option(gmg_handle h, const char* key, double value);
 int gmg_get_option(gmg_handle h, const char* key, double* value);
 
@@ -126,6 +132,9 @@ int gmg_get_convergence(gmg_handle h, double* t_ms, double* residue, int32_t* co
 /* ---- measurement support (not part of the reference surface) ----
  * Level sizes of the operators staged on the device: rows and stored entries of A_k, and of U_k. */
 int gmg_level_info(gmg_handle h, int32_t level, int64_t* rows, int64_t* nnz_a, int64_t* nnz_u);
+/* Jacobi dampings the smoother uses on a level for the system last reduced on the device:
+ * pre[pre_iters], post[post_iters] and the Gershgorin bound rho of D^-1 A_k they derive from. */
+int gmg_get_smoother_weights(gmg_handle h, int32_t level, double* rho, double* pre, double* post);
 /* CSR of the operator of a level as the device holds it (level 0: the staged lhs; k >= 1: the
  * Galerkin operator Abar[k], multigrid_solver.cpp:1389-1391). Sizes from gmg_level_info. */
 int gmg_get_level_matrix(gmg_handle h, int32_t level, int32_t* indptr, int32_t* indices, double* data);

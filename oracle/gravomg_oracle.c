@@ -40,6 +40,7 @@
 #include <time.h>
 
 #define ORC_MAX_LEVELS 16
+#define ORC_MAX_SWEEPS 16
 
 typedef struct {
     int rows, cols;
@@ -70,6 +71,7 @@ typedef struct orc_solver {
     /* parameters the binding sets (core.cpp:52-57) */
     int pre_iters, post_iters, max_iter, criterion, smoother; /* smoother 0 = GS (reference), 1 = damped Jacobi */
     double tol, omega;
+    double w_pre[ORC_MAX_LEVELS][ORC_MAX_SWEEPS], w_post[ORC_MAX_LEVELS][ORC_MAX_SWEEPS]; /* Jacobi damping per level and sweep */
     /* outputs */
     double t_reduction_ms, t_coarse_ms, t_cycles_ms, t_total_ms;
     int iterations;
@@ -224,10 +226,13 @@ void orc_gauss_seidel(int n, const int* cp, const int* ri, const double* v, cons
 
 /* Damped Jacobi, the sweep the device path substitutes: x' = x + (omega / A_kk) * (b - (A x)_k),
  * (A x)_k summed over the stored entries of column k (= row k, symmetric A) in stored order,
- * diagonal included. `tmp` is n x K scratch. Same association as the CUDA epilogue. */
+ * diagonal included. `tmp` is n x K scratch. Same association as the CUDA epilogue.
+ * omegas[it] is the damping of sweep `it` (a constant list is plain damped Jacobi; Chebyshev
+ * roots give the polynomial smoother the device uses by default). */
 void orc_jacobi(int n, const int* cp, const int* ri, const double* v, const double* rhs, double* x, double* tmp, int K,
-                int iters, double omega) {
+                int iters, const double* omegas) {
     for (int it = 0; it < iters; ++it) {
+        const double omega = omegas[it];
         for (int c = 0; c < K; ++c) {
             const double* xc = x + (size_t)c * n;
             const double* bc = rhs + (size_t)c * n;
@@ -470,6 +475,8 @@ orc_solver* orc_create(int n, const double* mass_diag) {
     /* Python defaults, core.py:10 */
     s->pre_iters = 2, s->post_iters = 2, s->max_iter = 100, s->criterion = 2, s->tol = 1e-4;
     s->smoother = 0, s->omega = 2.0 / 3.0;
+    for (int k = 0; k < ORC_MAX_LEVELS; ++k)
+        for (int i = 0; i < ORC_MAX_SWEEPS; ++i) s->w_pre[k][i] = s->w_post[k][i] = s->omega;
     return s;
 }
 
@@ -503,6 +510,16 @@ void orc_set_params(orc_solver* s, int pre_iters, int post_iters, int max_iter, 
                     double omega) {
     s->pre_iters = pre_iters, s->post_iters = post_iters, s->max_iter = max_iter, s->criterion = criterion;
     s->tol = tol, s->smoother = smoother, s->omega = omega;
+    for (int k = 0; k < ORC_MAX_LEVELS; ++k)
+        for (int i = 0; i < ORC_MAX_SWEEPS; ++i) s->w_pre[k][i] = s->w_post[k][i] = omega;
+}
+
+/* Per-sweep Jacobi damping of one level (pre- and post-smoothing sequences). */
+int orc_set_weights(orc_solver* s, int level, int n_pre, const double* pre, int n_post, const double* post) {
+    if (level < 0 || level >= ORC_MAX_LEVELS || n_pre > ORC_MAX_SWEEPS || n_post > ORC_MAX_SWEEPS) return 1;
+    for (int i = 0; i < n_pre; ++i) s->w_pre[level][i] = pre[i];
+    for (int i = 0; i < n_post; ++i) s->w_post[level][i] = post[i];
+    return 0;
 }
 
 /* "reduction" + "coarsest_solve" of multigrid_solver.cpp:1387-1401. */
@@ -526,12 +543,12 @@ int orc_setup(orc_solver* s, const int* cp, const int* ri, const double* v) {
     return status;
 }
 
-static void smooth(const orc_solver* s, const csc_t* A, const double* b, double* x, int K, int iters) {
+static void smooth(const orc_solver* s, const csc_t* A, const double* b, double* x, int K, int iters, const double* omegas) {
     if (s->smoother == 0) {
         orc_gauss_seidel(A->cols, A->colptr, A->rowidx, A->vals, b, x, K, iters);
     } else {
         double* tmp = (double*)malloc(sizeof(double) * (size_t)A->cols * K);
-        orc_jacobi(A->cols, A->colptr, A->rowidx, A->vals, b, x, tmp, K, iters, s->omega);
+        orc_jacobi(A->cols, A->colptr, A->rowidx, A->vals, b, x, tmp, K, iters, omegas);
         free(tmp);
     }
 }
@@ -547,7 +564,7 @@ static void vcycle(const orc_solver* s, const csc_t* A, const double* b, double*
     }
     const csc_t* U = &s->U[k];
     const int nc = U->cols;
-    smooth(s, A, b, x, K, s->pre_iters);
+    smooth(s, A, b, x, K, s->pre_iters, s->w_pre[k]);
     double* res = (double*)malloc(sizeof(double) * (size_t)n * K);
     orc_residual(n, A->colptr, A->rowidx, A->vals, b, x, res, K);
     double* rest = (double*)malloc(sizeof(double) * (size_t)nc * K);
@@ -561,7 +578,7 @@ static void vcycle(const orc_solver* s, const csc_t* A, const double* b, double*
         vcycle(s, &s->Abar[k + 1], rest, eps, K, k + 1);
     }
     orc_prolong_add(n, nc, U->colptr, U->rowidx, U->vals, eps, x, K);
-    smooth(s, A, b, x, K, s->post_iters);
+    smooth(s, A, b, x, K, s->post_iters, s->w_post[k]);
     free(res), free(rest), free(eps);
 }
 

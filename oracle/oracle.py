@@ -37,7 +37,8 @@ def _load():
     lib = C.CDLL(LIB_PATH)
     sig = {
         "orc_gauss_seidel": (None, [C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_int, C.c_int]),
-        "orc_jacobi": (None, [C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, C.c_int, C.c_int, C.c_double]),
+        "orc_jacobi": (None, [C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, C.c_int, C.c_int, _f64p]),
+        "orc_set_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f64p, C.c_int, _f64p]),
         "orc_residual": (None, [C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, C.c_int]),
         "orc_restrict": (None, [C.c_int, C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_int]),
         "orc_prolong_add": (None, [C.c_int, C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_int]),
@@ -107,13 +108,29 @@ def gauss_seidel(A, b, x, iters):
 
 
 def jacobi(A, b, x, iters, omega):
-    """``iters`` damped-Jacobi sweeps x += omega D^-1 (b - A x) (the device smoother)."""
+    """``iters`` damped-Jacobi sweeps x += omega_i D^-1 (b - A x) (the device smoother).
+    ``omega`` is one damping factor or a sequence with one entry per sweep."""
     n = A.shape[0]
     cp, ri, v = _csc(A)
     bb, xx = _colmajor(b, n), _colmajor(x, n)
     tmp = np.empty_like(xx)
-    lib().orc_jacobi(n, _i(cp), _i(ri), _d(v), _d(bb), _d(xx), _d(tmp), xx.shape[1], int(iters), float(omega))
+    om = np.ascontiguousarray(np.broadcast_to(np.asarray(omega, dtype=np.float64), (int(iters),)))
+    lib().orc_jacobi(n, _i(cp), _i(ri), _d(v), _d(bb), _d(xx), _d(tmp), xx.shape[1], int(iters), _d(om))
     return np.ascontiguousarray(xx)
+
+
+def chebyshev_weights(rho, alpha, degree):
+    """Jacobi damping factors 1/root_j of the degree-``degree`` Chebyshev polynomial on
+    [rho/alpha, rho] (the eigenvalue band of D^-1 A the smoother is asked to damp)."""
+    lo, hi = rho / alpha, rho
+    j = np.arange(degree)
+    return 1.0 / (0.5 * (hi + lo) + 0.5 * (hi - lo) * np.cos(np.pi * (2 * j + 1) / (2 * degree)))
+
+
+def gershgorin_rho(A):
+    """max_i sum_j |a_ij| / a_ii: an upper bound of the spectral radius of D^-1 A."""
+    A = sp.csr_matrix(A)
+    return float((np.asarray(abs(A).sum(1)).ravel() / A.diagonal()).max())
 
 
 def residual(A, b, x):
@@ -164,7 +181,7 @@ class OracleSolver:
     ``'jacobi'`` is the op-for-op counterpart of the device path."""
 
     def __init__(self, mass, U, pre_iters=2, post_iters=2, max_iter=100, stopping_criteria=2, tolerance=1e-4,
-                 smoother="gs", omega=2.0 / 3.0):
+                 smoother="gs", omega=2.0 / 3.0, weights=None):
         m = mass.diagonal() if sp.issparse(mass) else np.asarray(mass)
         self.mass = np.ascontiguousarray(m, dtype=np.float64)
         self.n = self.mass.shape[0]
@@ -178,6 +195,12 @@ class OracleSolver:
         lib().orc_set_params(self._h, int(pre_iters), int(post_iters), int(max_iter), int(stopping_criteria),
                              float(tolerance), {"gs": 0, "jacobi": 1}[smoother], float(omega))
         self.convergence = []
+        if weights is not None:  # {level: (pre_omegas, post_omegas)}
+            for level, (pre, post) in dict(weights).items():
+                pre = np.ascontiguousarray(pre, dtype=np.float64)
+                post = np.ascontiguousarray(post, dtype=np.float64)
+                if lib().orc_set_weights(self._h, int(level), len(pre), _d(pre), len(post), _d(post)):
+                    raise ValueError("bad smoother weights")
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -34,6 +34,20 @@ def _staged(p, K, lhs=None, rhs=None, **kw):
     return s, lhs, rhs
 
 
+def _weights(binding, n_levels):
+    """{level: (pre, post)} Jacobi dampings the device used (after a solve or a level_op)."""
+    out = {}
+    for k in range(n_levels):
+        _, pre, post = binding.smoother_weights(k)
+        out[k] = (pre, post)
+    return out
+
+
+def _jacobi_oracle(p, solver, **kw):
+    """The oracle running the device's own cycle: Jacobi sweeps with the device's dampings."""
+    return oracle.OracleSolver(p.M, p.U, smoother="jacobi", weights=_weights(solver.solver, len(p.U)), **kw)
+
+
 def _device_levels(s, n_levels):
     return [s.level_matrix(k) for k in range(n_levels + 1)]
 
@@ -50,18 +64,21 @@ def _rel_inf(a, b):
 
 
 # ------------------------------------------------------------------------------ P1: operators
-@pytest.mark.parametrize("path", [0, 1])
+@pytest.mark.parametrize("mode", ["staged-exact", "staged-auto", "direct"])
 @pytest.mark.parametrize("K", [1, 3])
-def test_p1_operators_match_the_oracle(ico_small, path, K):
+@pytest.mark.parametrize("smoother", ["chebyshev", "jacobi"])
+def test_p1_operators_match_the_oracle(ico_small, mode, K, smoother):
     p = ico_small
-    s, lhs, _ = _staged(p, K)
-    s.set_option("kernel_path", path)
+    s, lhs, _ = _staged(p, K, smoother=smoother)
+    s.set_option("kernel_path", 1 if mode == "direct" else 0)
+    s.set_option("lanes", 1 if mode == "staged-exact" else 0)
     s.stage(lhs, np.zeros((lhs.shape[0], K)))  # re-plan with the chosen kernel path
     L = len(p.U)
     rng = np.random.default_rng(5)
     s.level_op("residual", 0, np.zeros((lhs.shape[0], K)), np.zeros((lhs.shape[0], K)))  # triggers the reduction
     A = _device_levels(s, L)
-    exact = path == 0
+    W = _weights(s, L)
+    exact = mode == "staged-exact"
 
     def check(got, want):
         if exact:
@@ -75,8 +92,9 @@ def test_p1_operators_match_the_oracle(ico_small, path, K):
         b = rng.standard_normal((n, K))
         check(s.level_op("residual", k, x, b), oracle.residual(A[k], b, x))
         if k < L:
-            for sweeps in (1, 2, 3):
-                check(s.level_op("jacobi", k, x, b, sweeps=sweeps), oracle.jacobi(_rows(A[k]), b, x, sweeps, OMEGA))
+            for sweeps in (1, 2, 3):  # level_op cycles through the pre-smoothing dampings
+                om = [W[k][0][i % len(W[k][0])] for i in range(sweeps)]
+                check(s.level_op("jacobi", k, x, b, sweeps=sweeps), oracle.jacobi(_rows(A[k]), b, x, sweeps, om))
             U = p.U[k]
             e = rng.standard_normal((U.shape[1], K))
             check(s.level_op("restrict", k, x), oracle.restrict(U, x))
@@ -88,13 +106,14 @@ def test_p1_operators_on_a_larger_mesh(torus_mid, path):
     p = torus_mid
     s, lhs, _ = _staged(p, 1)
     s.set_option("kernel_path", path)
+    s.set_option("lanes", 1)
     s.stage(lhs, np.zeros((lhs.shape[0], 1)))
     rng = np.random.default_rng(6)
     n = lhs.shape[0]
     x = rng.standard_normal((n, 1))
     b = rng.standard_normal((n, 1))
     got = s.level_op("jacobi", 0, x, b, sweeps=2)
-    want = oracle.jacobi(lhs, b, x, 2, OMEGA)
+    want = oracle.jacobi(lhs, b, x, 2, _weights(s, 1)[0][0])
     if path == 0:
         np.testing.assert_array_equal(got, want)
     else:
@@ -150,15 +169,49 @@ def test_p1_coarse_solve(ico_small):
     assert backward <= 1e-13
 
 
+def test_smoother_weights_are_chebyshev_roots_on_the_gershgorin_band(ico_small):
+    p = ico_small
+    s, lhs, _ = _staged(p, 1, pre_iters=3, post_iters=2, cheb_alpha=8.0)
+    s.level_op("residual", 0, np.zeros((lhs.shape[0], 1)), np.zeros((lhs.shape[0], 1)))
+    A = _device_levels(s, len(p.U))
+    for k in range(len(p.U)):
+        rho, pre, post = s.smoother_weights(k)
+        assert rho == pytest.approx(oracle.gershgorin_rho(A[k]), rel=1e-14)
+        np.testing.assert_allclose(pre, oracle.chebyshev_weights(rho, 8.0, 3), rtol=1e-13)
+        np.testing.assert_allclose(post, oracle.chebyshev_weights(rho, 8.0, 2)[::-1], rtol=1e-13)
+        assert (pre > 0).all() and (pre * rho < 8.0 + 1e-9).all() and (pre * rho >= 1.0 - 1e-12).all()
+    s2, _, _ = _staged(p, 1, smoother="jacobi", omega=0.7)
+    s2.level_op("residual", 0, np.zeros((lhs.shape[0], 1)), np.zeros((lhs.shape[0], 1)))
+    _, pre, post = s2.smoother_weights(0)
+    np.testing.assert_array_equal(np.concatenate([pre, post]), 0.7)
+
+
+def test_chebyshev_smoother_needs_fewer_cycles_than_fixed_jacobi(torus_mid):
+    """Cycle counts to 1e-6 next to the reference algorithm's (Gauss-Seidel) count."""
+    p = torus_mid
+    counts = {}
+    for smoother in ("jacobi", "chebyshev"):
+        s = p.new_solver(tolerance=1e-6, smoother=smoother)
+        s.solve(p.lhs, p.rhs)
+        counts[smoother] = int(s.solver_timing["iterations"])
+    og = oracle.OracleSolver(p.M, p.U, tolerance=1e-6, smoother="gs")
+    og.solve(p.lhs, p.rhs)
+    counts["reference gs"] = int(og.solver_timing["iterations"])
+    print("\ncycles to 1e-6:", counts)
+    assert counts["chebyshev"] < counts["jacobi"]
+    assert counts["chebyshev"] <= 2 * counts["reference gs"]
+
+
 # ------------------------------------------------------------------------------ P2: one cycle
 @pytest.mark.parametrize("K", [1, 3])
-def test_p2_one_vcycle_matches_the_oracle_jacobi_cycle(ico_small, K):
+@pytest.mark.parametrize("smoother", ["chebyshev", "jacobi"])
+def test_p2_one_vcycle_matches_the_oracle_jacobi_cycle(ico_small, K, smoother):
     p = ico_small
     lhs = (p.M + 1e-3 * p.S).tocsr()
     rhs = (p.M @ p.V)[:, :K]
-    solver = p.new_solver(max_iter=1)
+    solver = p.new_solver(max_iter=1, smoother=smoother)
     x = solver.solve(lhs, rhs)
-    o = oracle.OracleSolver(p.M, p.U, smoother="jacobi", omega=OMEGA, max_iter=1)
+    o = _jacobi_oracle(p, solver, max_iter=1)
     want = o.solve(lhs, rhs)
     assert np.linalg.norm(x - want) <= 1e-12 * np.linalg.norm(want)
     assert solver.solver_timing["iterations"] == 1
@@ -169,7 +222,7 @@ def test_p2_one_vcycle_poisson(ico_small):
     p = ico_small
     solver = p.new_solver(max_iter=1)
     x = solver.solve(p.lhs, p.rhs)
-    o = oracle.OracleSolver(p.M, p.U, smoother="jacobi", omega=OMEGA, max_iter=1)
+    o = _jacobi_oracle(p, solver, max_iter=1)
     want = o.solve(p.lhs, p.rhs)
     # rounding floor of A x for |x| ~ mean(rhs)/tau (see tests/test_oracle.py)
     bound = 4 * EPS * abs(p.lhs).sum(0).max() * np.linalg.norm(want)
@@ -187,7 +240,7 @@ def test_p3_solve_reaches_the_tolerance_like_the_reference(request, fixture, tol
 
     # the same cycle on the CPU (Jacobi variant): same residual history down to the rounding
     # floor of forming A x (|x| ~ mean(rhs)/tau for the Poisson system, see tests/test_oracle.py)
-    oj = oracle.OracleSolver(p.M, p.U, tolerance=tol, smoother="jacobi", omega=OMEGA)
+    oj = _jacobi_oracle(p, solver, tolerance=tol)
     xj = oj.solve(p.lhs, p.rhs)
     hist_j = [r for _, r in oj.convergence]
     assert int(t["iterations"]) == len(hist)
@@ -202,9 +255,9 @@ def test_p3_solve_reaches_the_tolerance_like_the_reference(request, fixture, tol
     rhs = p.rhs
     res_gpu = oracle.residual_check(p.lhs, rhs, x, 2, p.m)  # judged by the oracle's norm
     res_ref = og.solver_timing["residue"]
-    assert res_gpu <= tol and res_ref <= tol and t["residue"] == pytest.approx(res_gpu, rel=1e-6)
+    assert res_gpu <= tol and res_ref <= tol and abs(t["residue"] - res_gpu) <= 1e-6 * res_gpu + floor
     assert all(a > b for a, b in zip(hist, hist[1:]))  # P4: monotone
-    print(f"\n[{fixture} tol={tol:g}] cycles gpu(jacobi)={len(hist)} ref(gs)={int(og.solver_timing['iterations'])} "
+    print(f"\n[{fixture} tol={tol:g}] cycles gpu(chebyshev-jacobi)={len(hist)} ref(gs)={int(og.solver_timing['iterations'])} "
           f"residual-norm ratio gpu/ref={res_gpu / res_ref:.3f}")
 
     # both agree with a sparse direct solve in the norm the residual controls
@@ -278,7 +331,7 @@ def test_at_least_one_cycle_max_iter_and_initial_guess(ico_small):
     x3 = s.solve(p.lhs, p.rhs)
     assert s.solver_timing["iterations"] == 3 and len(s.convergence) == 3
     # x0 = rhs (core.cpp:69): three oracle cycles from x0 = rhs land on the same iterate
-    o = oracle.OracleSolver(p.M, p.U, smoother="jacobi", omega=OMEGA, tolerance=0.0, max_iter=3)
+    o = _jacobi_oracle(p, s, tolerance=0.0, max_iter=3)
     want = o.solve(p.lhs, p.rhs)
     bound = 8 * EPS * abs(p.lhs).sum(0).max() * np.linalg.norm(want)
     assert np.linalg.norm(p.lhs @ (x3 - want)) <= bound
@@ -319,7 +372,7 @@ def test_float32_smoother_levels(ico10k):
     rng = np.random.default_rng(3)
     x = rng.standard_normal(rhs.shape)
     got = b.level_op("jacobi", 0, x, rhs, sweeps=1)
-    want = oracle.jacobi(lhs, rhs, x, 1, OMEGA)
+    want = oracle.jacobi(lhs, rhs, x, 1, b.smoother_weights(0)[1][:1])
     assert _rel_inf(got, want) <= 2e-6
 
 
@@ -400,7 +453,7 @@ def test_error_behaviour(ico_small):
     x = s.solve(p.lhs, p.rhs)
     assert s.solver_timing["residue"] <= 1e-4
     # a diverging smoother is reported, not returned
-    d = p.new_solver(omega=2.5, max_iter=100)
+    d = p.new_solver(smoother="jacobi", omega=2.5, max_iter=100)
     with pytest.raises(RuntimeError, match="diverged|non-finite"):
         d.solve(p.lhs, p.rhs)
 
