@@ -165,6 +165,7 @@ def main():
     ap.add_argument("--cheb-alpha", type=float, default=10.0)
     ap.add_argument("--sweeps", type=int, default=2, help="pre and post sweeps per level")
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--pdl", type=int, default=1)
     ap.add_argument("--loop-mode", type=int, default=1)
     ap.add_argument("--kernel-path", type=int, default=0)
     ap.add_argument("--use-graph", type=int, default=1)
@@ -229,6 +230,7 @@ def main():
     b.set_option("kernel_path", args.kernel_path)
     b.set_option("use_graph", args.use_graph)
     b.set_option("lanes", args.lanes)
+    b.set_option("pdl", args.pdl)
     U = solver.prolongation_matrices
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 

@@ -150,6 +150,7 @@ int gmg_set_option(gmg_handle h, const char* key, double value) {
         else if (k == "use_graph") s.use_graph = value != 0.0;
         else if (k == "loop_mode") s.loop_mode = (int)value;
         else if (k == "profile") s.profile = value != 0.0;
+        else if (k == "pdl") s.use_pdl = value != 0.0, cycle = true;
         else if (k == "kernel_path") s.kernel_path = (int)value, hierarchy = true;
         else throw std::invalid_argument("unknown option: " + k);
         require(s.params.pre_iters >= 0 && s.params.post_iters >= 0 && s.params.pre_iters <= 16 && s.params.post_iters <= 16, "sweep counts must be 0..16");
@@ -180,6 +181,7 @@ int gmg_get_option(gmg_handle h, const char* key, double* value) {
         else if (k == "use_graph") *value = s.use_graph;
         else if (k == "loop_mode") *value = s.loop_mode;
         else if (k == "profile") *value = s.profile;
+        else if (k == "pdl") *value = s.use_pdl;
         else if (k == "kernel_path") *value = s.kernel_path;
         else throw std::invalid_argument("unknown option: " + k);
     });

@@ -19,40 +19,47 @@ struct GemmTask {
     double alpha, beta;
 };
 
+constexpr int KC = 64;  // k-chunk staged in shared memory: one round of global loads per 64 k-steps
+constexpr size_t kGemmSmem = 2 * (size_t)KC * (NB + 1) * sizeof(double);
+constexpr size_t kPotrfSmem = (3 * (size_t)NB * (NB + 1) + NB + 2 * NB + 2 + NB) * sizeof(double);
+
 template <bool TRANS_B>
 __global__ void __launch_bounds__(256) gemm_tile_kernel(const GemmTask* __restrict__ tasks) {
     const GemmTask t = tasks[blockIdx.x];
-    __shared__ double As[16][NB + 2];
-    __shared__ double Bs[16][NB + 2];
+    extern __shared__ double gsm[];
+    double(*As)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(gsm);
+    double(*Bs)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(gsm + KC * (NB + 1));
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;  // rows 4*tx.., cols 4*ty..
+    const int tx = tid & 15, ty = tid >> 4;  // rows tx + 16 i, cols ty + 16 j (conflict-free shared reads)
     double acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
-    for (int kc = t.k0; kc < t.k1; kc += 16) {
+    for (int kc = t.k0; kc < t.k1; kc += KC) {
+        const int kn = min(KC, t.k1 - kc);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int e = tid + 256 * i;
+        for (int it = 0; it < KC * NB / 256; ++it) {
+            const int e = tid + 256 * it;
             const int m = e & 63, k = e >> 6;
-            As[k][m] = t.A[m + (size_t)(kc + k) * t.lda];
-            if (TRANS_B) {
-                Bs[k][m] = t.B[m + (size_t)(kc + k) * t.ldb];  // B[n, k]
-            } else {
-                const int kk = e & 15, n = e >> 4;
-                Bs[kk][n] = t.B[(kc + kk) + (size_t)n * t.ldb];  // B[k, n]
+            if (k < kn) {
+                As[k][m] = t.A[m + (size_t)(kc + k) * t.lda];
+                if (TRANS_B) Bs[k][m] = t.B[m + (size_t)(kc + k) * t.ldb];  // B[n, k]
+            }
+            if (!TRANS_B) {
+                const int kk = e & 63, n = e >> 6;
+                if (kk < kn) Bs[kk][n] = t.B[(kc + kk) + (size_t)n * t.ldb];  // B[k, n]
             }
         }
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
+#pragma unroll 8
+        for (int k = 0; k < kn; ++k) {
             double a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[k][4 * tx + i];
+            for (int i = 0; i < 4; ++i) a[i] = As[k][tx + 16 * i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[k][4 * ty + j];
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k][ty + 16 * j];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -62,63 +69,183 @@ __global__ void __launch_bounds__(256) gemm_tile_kernel(const GemmTask* __restri
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        double* c = t.C + (size_t)(4 * ty + j) * t.ldc + 4 * tx;
+        double* c = t.C + (size_t)(ty + 16 * j) * t.ldc;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const double v = t.alpha * acc[i][j];
-            c[i] = (t.beta == 0.0) ? v : fma(t.beta, c[i], v);
+            double* ce = c + tx + 16 * i;
+            *ce = (t.beta == 0.0) ? v : fma(t.beta, *ce, v);
         }
     }
 }
 
-// Cholesky of one 64x64 diagonal block in shared memory, plus the inverse of its factor.
+// Cholesky of one 64x64 diagonal block plus the inverse of its factor, one CTA of 256 threads.
 // A (lower part read) -> L_jj written back to A (upper part zeroed); inv(L_jj) -> W block.
+//   factor   right-looking on the unscaled columns: step k subtracts S[r][k] S[c][k] / S[k][k]
+//            from the trailing lower triangle (one barrier per step, no serial sqrt/scale phase);
+//            columns are scaled by 1/sqrt(pivot) once at the end.
+//   inverse  the four 16x16 diagonal sub-blocks by forward substitution (one thread per column,
+//            chains of <= 120 steps), then two doubling steps W21 = -W22 (L21 W11) as small
+//            shared-memory products spread over all threads.
+// Compact loops on purpose: a fully unrolled register version is instruction-fetch bound.
+// 1/x to double precision without the long IEEE division sequence: single-precision seed and two
+// Newton steps (relative error ~1e-16 for the well-scaled positive pivots this is used on).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r = (double)__frcp_rn((float)x);
+    r = r * fma(-x, r, 2.0);
+    r = r * fma(-x, r, 2.0);
+    return r;
+}
+
+#ifdef GMG_POTRF_CLK
+__device__ long long g_potrf_clk[8];
+#define POTRF_CLK(i) do { if (threadIdx.x == 0) g_potrf_clk[i] = clock64(); } while (0)
+#else
+#define POTRF_CLK(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double* A, double* W, int ld, int j0, CycleControl* ctl) {
-    extern __shared__ double sm[];
-    double(*S)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);
-    double(*X)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm + NB * (NB + 1));
+    extern __shared__ double psm[];
+    double(*S)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(psm);
+    double(*X)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(psm + NB * (NB + 1));
+    double(*T)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(psm + 2 * NB * (NB + 1));
+    double* dd = psm + 3 * NB * (NB + 1);
     const int tid = threadIdx.x;
     double* Ajj = A + j0 + (size_t)j0 * ld;
     double* Wjj = W + j0 + (size_t)j0 * ld;
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int r = e & 63, c = e >> 6;
-        S[r][c] = Ajj[r + (size_t)c * ld];
-        X[r][c] = 0.0;
+    // ---- factor: thread (ty, tx) keeps the 4 x 4 entries (ty + 16 i, tx + 16 j) in registers; per
+    // step only column k and the reciprocal pivot travel through shared memory (double-buffered,
+    // one barrier per step), everything else is register arithmetic.
+    double* colk = dd + NB;        // [2][NB]
+    double* pinv = colk + 2 * NB;  // [2]
+    double* pivots = pinv + 2;     // [NB]
+    const int tx = tid & 15, ty = tid >> 4;
+    double a[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rr = ty + 16 * i, cc = tx + 16 * j;
+            a[i][j] = rr >= cc ? Ajj[rr + (size_t)cc * ld] : 0.0;
+        }
+    for (int e = tid; e < NB * NB; e += 256) X[e & 63][e >> 6] = 0.0;
+    POTRF_CLK(0);
+    // publish column 0 and 1 / pivot 0
+    if (tx == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) colk[ty + 16 * i] = a[i][0];
+        if (ty == 0) pinv[0] = fast_rcp(a[0][0]), pivots[0] = a[0][0];
     }
     __syncthreads();
-    for (int k = 0; k < NB; ++k) {
-        if (tid == 0) {
-            double d = S[k][k];
-            if (!(d > 0.0) || d > 1.7976931348623157e308) {
-                atomicOr(&ctl->error, 4);
-                d = 1.0;
+    for (int k = 0; k < NB - 1; ++k) {
+        const double* ck = colk + (k & 1) * NB;
+        double* cn = colk + ((k + 1) & 1) * NB;
+        const double pi = pinv[k & 1];
+        double lr[4], lc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) lr[i] = ck[ty + 16 * i] * pi;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) lc[j] = ck[tx + 16 * j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rr = ty + 16 * i, cc = tx + 16 * j;
+                if (cc > k && rr >= cc) a[i][j] = fma(-lr[i], lc[j], a[i][j]);
             }
-            S[k][k] = sqrt(d);
-        }
-        __syncthreads();
-        if (tid > k && tid < NB) S[tid][k] /= S[k][k];
-        __syncthreads();
-        for (int e = tid; e < NB * NB; e += 256) {
-            const int r = e & 63, c = e >> 6;
-            if (c > k && r >= c) S[r][c] = fma(-S[r][k], S[c][k], S[r][c]);
+        // owners of column k + 1 publish it (it is final now) together with its reciprocal pivot
+        const int kn = k + 1;
+        if (tx == (kn & 15)) {
+            const int jn = kn >> 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double v = jn == 0 ? a[i][0] : jn == 1 ? a[i][1] : jn == 2 ? a[i][2] : a[i][3];
+                cn[ty + 16 * i] = v;
+                if (ty + 16 * i == kn) pinv[kn & 1] = fast_rcp(v), pivots[kn] = v;
+            }
         }
         __syncthreads();
     }
-    if (tid < NB) {  // column tid of inv(L): forward substitution against e_tid
-        const int c = tid;
-        X[c][c] = 1.0 / S[c][c];
-        for (int i = c + 1; i < NB; ++i) {
-            double s = 0.0;
-            for (int m = c; m < i; ++m) s = fma(S[i][m], X[m][c], s);
-            X[i][c] = -s / S[i][i];
+    POTRF_CLK(1);
+    // ---- scale the columns by 1 / sqrt(pivot) and put L into shared memory for the inverse
+    if (tid < NB) {
+        double d = pivots[tid];
+        if (!(d > 0.0) || d > 1.7976931348623157e308) {
+            atomicOr(&ctl->error, 4);
+            d = 1.0;
+        }
+        dd[tid] = sqrt(d);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rr = ty + 16 * i, cc = tx + 16 * j;
+            S[rr][cc] = rr > cc ? a[i][j] / dd[cc] : (rr == cc ? dd[cc] : 0.0);
+        }
+    __syncthreads();
+    POTRF_CLK(2);
+    // ---- inverse of the lower-triangular S into X
+    if (tid < NB) dd[tid] = 1.0 / S[tid][tid];  // reciprocal diagonal of L
+    __syncthreads();
+    if (tid < NB) {  // 16x16 diagonal sub-blocks: column c of block b
+        const int b0 = tid & ~15, c = tid;
+        X[c][c] = dd[c];
+        for (int i = c + 1; i < b0 + 16; ++i) {
+            double acc0 = 0.0, acc1 = 0.0;
+            int m = c;
+            for (; m + 1 < i; m += 2) {
+                acc0 = fma(S[i][m], X[m][c], acc0);
+                acc1 = fma(S[i][m + 1], X[m + 1][c], acc1);
+            }
+            if (m < i) acc0 = fma(S[i][m], X[m][c], acc0);
+            X[i][c] = -(acc0 + acc1) * dd[i];
         }
     }
     __syncthreads();
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int r = e & 63, c = e >> 6;
-        Ajj[r + (size_t)c * ld] = r >= c ? S[r][c] : 0.0;
-        Wjj[r + (size_t)c * ld] = r >= c ? X[r][c] : 0.0;
+    POTRF_CLK(3);
+    for (int b = 16; b < NB; b *= 2) {
+        // for every pair of adjacent b x b diagonal blocks at offset o: T = L21 * W11, then W21 = -W22 * T
+        const int per_pair = b * b, pairs = NB / (2 * b);
+        for (int e = tid; e < pairs * per_pair; e += 256) {
+            const int p = e / per_pair, q = e % per_pair;
+            const int i = q % b, j = q / b, o = p * 2 * b;
+            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+            int m = j;  // W11 lower: m >= j
+            for (; m + 3 < b; m += 4) {
+                acc0 = fma(S[o + b + i][o + m], X[o + m][o + j], acc0);
+                acc1 = fma(S[o + b + i][o + m + 1], X[o + m + 1][o + j], acc1);
+                acc2 = fma(S[o + b + i][o + m + 2], X[o + m + 2][o + j], acc2);
+                acc3 = fma(S[o + b + i][o + m + 3], X[o + m + 3][o + j], acc3);
+            }
+            for (; m < b; ++m) acc0 = fma(S[o + b + i][o + m], X[o + m][o + j], acc0);
+            T[o + b + i][o + j] = (acc0 + acc1) + (acc2 + acc3);
+        }
+        __syncthreads();
+        for (int e = tid; e < pairs * per_pair; e += 256) {
+            const int p = e / per_pair, q = e % per_pair;
+            const int i = q % b, j = q / b, o = p * 2 * b;
+            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+            int m = 0;  // W22 lower: m <= i
+            for (; m + 3 <= i; m += 4) {
+                acc0 = fma(X[o + b + i][o + b + m], T[o + b + m][o + j], acc0);
+                acc1 = fma(X[o + b + i][o + b + m + 1], T[o + b + m + 1][o + j], acc1);
+                acc2 = fma(X[o + b + i][o + b + m + 2], T[o + b + m + 2][o + j], acc2);
+                acc3 = fma(X[o + b + i][o + b + m + 3], T[o + b + m + 3][o + j], acc3);
+            }
+            for (; m <= i; ++m) acc0 = fma(X[o + b + i][o + b + m], T[o + b + m][o + j], acc0);
+            X[o + b + i][o + j] = -((acc0 + acc1) + (acc2 + acc3));
+        }
+        __syncthreads();
     }
+    POTRF_CLK(4);
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int rr = e & 63, cc = e >> 6;
+        Ajj[rr + (size_t)cc * ld] = S[rr][cc];  // upper part is zero
+        Wjj[rr + (size_t)cc * ld] = rr >= cc ? X[rr][cc] : 0.0;
+    }
+    POTRF_CLK(5);
 }
 
 __global__ void pad_identity_kernel(double* A, int ld, int n, int npad) {
@@ -202,8 +329,9 @@ void DenseCoarseSolver::setup(int n, cudaStream_t stream) {
     Wt_.ensure(elems);
     tmp_.ensure(elems);
     y_.ensure((size_t)npad_ * kMaxRhsTile);
-    GMG_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(2 * NB * (NB + 1) * sizeof(double))));
+    GMG_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem));
+    GMG_CUDA(cudaFuncSetAttribute(gemm_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    GMG_CUDA(cudaFuncSetAttribute(gemm_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
 
     const int ld = npad_;
     std::vector<GemmTask> tasks;
@@ -254,10 +382,22 @@ void DenseCoarseSolver::setup(int n, cudaStream_t stream) {
 }
 
 void DenseCoarseSolver::factor(const int* rowptr, const int* colidx, const double* vals, CycleControl* ctl,
-                               cudaStream_t stream) {
+                               cudaStream_t stream, bool profile) {
     const int ld = npad_;
     const size_t bytes = (size_t)npad_ * npad_ * sizeof(double);
     int launches = 0;
+    // optional phase timing (debug aid, prints to stderr): 0 densify, 1 potrf, 2 panel, 3 update, 4 inverse, 5 transpose
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> ev_phase;
+    auto mark = [&](int phase) {
+        if (!profile) return;
+        cudaEvent_t e;
+        GMG_CUDA(cudaEventCreate(&e));
+        GMG_CUDA(cudaEventRecord(e, stream));
+        ev.push_back(e);
+        ev_phase.push_back(phase);
+    };
+    mark(0);
     GMG_CUDA(cudaMemsetAsync(L_.ptr, 0, bytes, stream));
     GMG_CUDA(cudaMemsetAsync(W_.ptr, 0, bytes, stream));
     launch_csr_to_dense(n_, rowptr, colidx, vals, L_.ptr, ld, stream);
@@ -267,29 +407,46 @@ void DenseCoarseSolver::factor(const int* rowptr, const int* colidx, const doubl
         ++launches;
     }
     const GemmTask* tasks = reinterpret_cast<const GemmTask*>(tasks_.ptr);
-    const size_t potrf_smem = 2 * NB * (NB + 1) * sizeof(double);
     for (int j = 0; j < nb_; ++j) {
-        potrf_diag_kernel<<<1, 256, potrf_smem, stream>>>(L_.ptr, W_.ptr, ld, NB * j, ctl);
+        mark(1);
+        potrf_diag_kernel<<<1, 256, kPotrfSmem, stream>>>(L_.ptr, W_.ptr, ld, NB * j, ctl);
         ++launches;
+        mark(2);
         if (chol_panel_[j].count) {
-            gemm_tile_kernel<true><<<chol_panel_[j].count, 256, 0, stream>>>(tasks + chol_panel_[j].first);
+            gemm_tile_kernel<true><<<chol_panel_[j].count, 256, kGemmSmem, stream>>>(tasks + chol_panel_[j].first);
             ++launches;
         }
+        mark(3);
         if (chol_update_[j].count) {
-            gemm_tile_kernel<true><<<chol_update_[j].count, 256, 0, stream>>>(tasks + chol_update_[j].first);
+            gemm_tile_kernel<true><<<chol_update_[j].count, 256, kGemmSmem, stream>>>(tasks + chol_update_[j].first);
             ++launches;
         }
     }
+    mark(4);
     for (size_t s = 0; s < inv_first_.size(); ++s) {
-        gemm_tile_kernel<false><<<inv_first_[s].count, 256, 0, stream>>>(tasks + inv_first_[s].first);
-        gemm_tile_kernel<false><<<inv_second_[s].count, 256, 0, stream>>>(tasks + inv_second_[s].first);
+        gemm_tile_kernel<false><<<inv_first_[s].count, 256, kGemmSmem, stream>>>(tasks + inv_first_[s].first);
+        gemm_tile_kernel<false><<<inv_second_[s].count, 256, kGemmSmem, stream>>>(tasks + inv_second_[s].first);
         launches += 2;
     }
+    mark(5);
     dim3 tgrid((npad_ + 31) / 32, (npad_ + 31) / 32), tblock(32, 8);
     transpose_kernel<<<tgrid, tblock, 0, stream>>>(W_.ptr, Wt_.ptr, npad_, ld);
     ++launches;
+    mark(6);
     GMG_CUDA(cudaGetLastError());
     factor_launches_ = launches;
+    if (profile) {
+        GMG_CUDA(cudaStreamSynchronize(stream));
+        double tot[6] = {0, 0, 0, 0, 0, 0};
+        for (size_t i = 0; i + 1 < ev.size(); ++i) {
+            float ms = 0;
+            GMG_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+            tot[ev_phase[i]] += ms;
+        }
+        std::fprintf(stderr, "[gravomg_b200] coarse factor n=%d: densify %.1f us, potrf %.1f, panel %.1f, update %.1f, inverse %.1f, transpose %.1f\n",
+                     n_, 1e3 * tot[0], 1e3 * tot[1], 1e3 * tot[2], 1e3 * tot[3], 1e3 * tot[4], 1e3 * tot[5]);
+        for (auto e : ev) cudaEventDestroy(e);
+    }
 }
 
 void DenseCoarseSolver::solve(const double* b, double* x, int K, int ld, const CycleControl* ctl, cudaStream_t stream) {

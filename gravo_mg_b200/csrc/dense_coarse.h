@@ -20,7 +20,8 @@ public:
     // Size the workspace for an n x n operator (idempotent for the same n).
     void setup(int n, cudaStream_t stream);
     // Densify the CSR operator and (re)compute L and W = L^-1. Sets ctl->error |= 4 on breakdown.
-    void factor(const int* rowptr, const int* colidx, const double* vals, CycleControl* ctl, cudaStream_t stream);
+    void factor(const int* rowptr, const int* colidx, const double* vals, CycleControl* ctl, cudaStream_t stream,
+                bool profile = false);
     // x = A^-1 b for K columns stored row-major with leading dimension ld. b and x may alias.
     void solve(const double* b, double* x, int K, int ld, const CycleControl* ctl, cudaStream_t stream);
     int size() const { return n_; }

@@ -24,7 +24,8 @@ template <typename T>
 struct DevMat {
     int rows = 0, cols = 0;
     int64_t nnz = 0;
-    DeviceBuffer<int> indptr, indices, rowidx, tiles;
+    DeviceBuffer<int> indptr, indices, rowidx;
+    DeviceBuffer<int4> tiles;
     DeviceBuffer<double> v64;
     DeviceBuffer<float> v32;
     SpmvPlan plan;
@@ -32,7 +33,7 @@ struct DevMat {
     const T* vals() const;
     void upload_pattern(const HostCsr& m, cudaStream_t s) {
         rows = (int)m.rows, cols = (int)m.cols, nnz = m.nnz();
-        indptr.upload(m.indptr, s);
+        indptr.upload(m.indptr, s, 8);
         indices.upload(m.indices.data(), m.indices.size(), s, 8);
         v64.ensure(nnz, 8);
         GMG_CUDA(cudaMemsetAsync(v64.ptr, 0, (nnz + 8) * sizeof(double), s));
@@ -63,20 +64,25 @@ struct DevMat {
             // threads per row of the staged kernel: enough rows per tile to keep the CTA busy, few
             // enough entries per tile that many CTAs fit one SM's shared memory
             int sl = staged_lanes;
-            if (sl == 0) sl = avg <= 5.0 ? 1 : avg <= 12.0 ? 2 : avg <= 28.0 ? 4 : 8;
+            if (sl == 0) sl = avg <= 10.0 ? 1 : avg <= 26.0 ? 2 : avg <= 60.0 ? 4 : 8;  // measured: tools/spmv_lab.cu
             // stage budget: kStagedStages stages, at least two resident CTAs per SM
-            const size_t per_stage = (staged_smem_limit() / 2 - 1280) / kStagedStages;
+            const int stage_rows = kStagedThreads / sl;
+            const size_t per_stage = (staged_smem_limit() / 2 - 1280) / kStagedStages - 16 - (size_t)(stage_rows + 8) * sizeof(int);
             const int cap = (int)(per_stage / (sizeof(T) + sizeof(int))) & ~3;
             int worst = 0;
-            std::vector<int> t = plan_row_tiles(indptr_h, kStagedThreads / sl, cap, &worst);
+            std::vector<int> t = plan_row_tiles(indptr_h, stage_rows, cap, &worst);
             if (worst <= cap) {
-                tiles.upload(t, s);
+                std::vector<int4> desc(t.size() - 1);
+                for (size_t i = 0; i + 1 < t.size(); ++i)
+                    desc[i] = make_int4(t[i], t[i + 1], indptr_h[t[i]] & ~3, (indptr_h[t[i + 1]] + 3) & ~3);
+                tiles.upload(desc, s);
                 plan.path = 0;
                 plan.staged_lanes = sl;
-                plan.n_tiles = (int)t.size() - 1;
+                plan.n_tiles = (int)desc.size();
                 plan.stage_elems = std::max((worst + 3) & ~3, 4);
-                plan.tile_rows = tiles.ptr;
-                GMG_CUDA(cudaStreamSynchronize(s));  // `t` is a local
+                plan.stage_rows = stage_rows;
+                plan.tile_desc = tiles.ptr;
+                GMG_CUDA(cudaStreamSynchronize(s));  // `desc` is a local
             }
         }
     }
@@ -172,6 +178,7 @@ public:
     void solve_staged() override {
         GMG_CUDA(cudaSetDevice(st_->params.device));
         if (!staged_) throw std::logic_error("solve_staged before stage_system");
+        set_launch_pdl(st_->use_pdl);
         const gmg_params& p = st_->params;
         if (p.cycle_type != 0) throw std::invalid_argument("only cycle_type 0 (V-cycle) is implemented on the device path");
         if (p.max_iter < 1) throw std::invalid_argument("max_iter must be >= 1");
@@ -250,6 +257,7 @@ public:
         GMG_CUDA(cudaSetDevice(st_->params.device));
         if (n != st_->n) throw std::invalid_argument("lhs has a different number of rows than the point set of the constructor");
         if (type < 0 || type > 3) throw std::invalid_argument("residual type must be 0..3");
+        set_launch_pdl(st_->use_pdl);
         if (K < 1 || K > kMaxRhsTile * kMaxNormChunks) throw std::invalid_argument("number of right-hand sides must be 1..32");
         const int64_t nnz = indptr[n];
         q_indptr_.upload(indptr, n + 1, stream_);
@@ -317,7 +325,7 @@ public:
             ++launches;
         }
         if (after_reduction) GMG_CUDA(cudaEventRecord(after_reduction, stream_));
-        coarse_.factor(lv_[L].A.indptr.ptr, lv_[L].A.indices.ptr, lv_[L].A.v64.ptr, ctl_.ptr, stream_);
+        coarse_.factor(lv_[L].A.indptr.ptr, lv_[L].A.indices.ptr, lv_[L].A.v64.ptr, ctl_.ptr, stream_, st_->profile);
         launches += coarse_.launches_per_factor();
         numeric_ready_ = true;
         return launches;
@@ -348,6 +356,7 @@ public:
     void level_op(int kind, int level, const double* a, const double* b, double* out, int sweeps) override {
         GMG_CUDA(cudaSetDevice(st_->params.device));
         if (!staged_) throw std::logic_error("level_op before stage_system");
+        set_launch_pdl(st_->use_pdl);
         const int L = n_levels_;
         if (level < 0 || level > L) throw std::invalid_argument("level out of range");
         if (cycle_dirty_) build_cycle();

@@ -43,6 +43,7 @@ struct SolverState {
     int kernel_path = 0;             // 0 staged (TMA) where it fits, 1 direct everywhere
     int staged_lanes = 0;            // staged kernels: threads per row; 0 = from the mean row length
     bool profile = false;
+    bool use_pdl = true;             // programmatic dependent launch of the row-product kernels
     std::map<std::string, double> solver_timing;           // reference solverTiming keys
     std::vector<std::pair<double, double>> convergence;    // (elapsed ms, residue) per cycle
     int64_t last_launches = 0;

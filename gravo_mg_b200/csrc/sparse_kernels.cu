@@ -180,8 +180,8 @@ __global__ void csr_to_dense_kernel(int n, const int* __restrict__ rowptr, const
 }
 
 // ------------------------------------------------------------------ launchers
-size_t staged_smem_bytes(int stage_elems, size_t value_size) {
-    return 128 + (size_t)kStagedStages * stage_elems * (value_size + sizeof(int));
+size_t staged_smem_bytes(int stage_rows, int stage_elems, size_t value_size) {
+    return 128 + (size_t)kStagedStages * staged_stage_bytes(stage_rows, stage_elems, value_size);
 }
 
 size_t staged_smem_limit() {
@@ -198,6 +198,25 @@ size_t staged_smem_limit() {
 namespace {
 
 thread_local bool g_dry_run = false;
+thread_local bool g_use_pdl = true;
+
+// Launch with the programmatic-stream-serialization attribute: the kernel may begin (up to its
+// grid_dependency_wait()) while the previous kernel in the stream is still draining. Captured
+// into CUDA graphs as programmatic dependency edges.
+template <typename Kernel, typename Args>
+void launch_pdl(Kernel kernel, int grid, int block, size_t smem, cudaStream_t stream, const Args& args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3((unsigned)block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    GMG_CUDA(cudaLaunchKernelEx(&cfg, kernel, args));
+}
 
 int num_sms() {
     static int n = 0;
@@ -235,12 +254,12 @@ int resident_blocks(const void* kernel, int threads, size_t smem) {
 
 template <typename T, int K, int EPI, int LANES>
 int launch_staged(SpmvArgs<T>& a, const SpmvPlan& plan, cudaStream_t stream) {
-    const size_t smem = staged_smem_bytes(plan.stage_elems, sizeof(T));
+    const size_t smem = staged_smem_bytes(plan.stage_rows, plan.stage_elems, sizeof(T));
     auto kernel = spmv_staged_kernel<T, K, EPI, LANES>;
-    const int per_sm = resident_blocks((const void*)kernel, kStagedThreads, smem);
+    const int per_sm = resident_blocks((const void*)kernel, kStagedThreads + 32, smem);
     int grid = std::min(std::max(plan.n_tiles, 1), per_sm * num_sms());
     if (EPI == EPI_NORM) grid = std::min(grid, kMaxNormBlocks);
-    if (!g_dry_run) kernel<<<grid, kStagedThreads, smem, stream>>>(a);
+    if (!g_dry_run) launch_pdl(kernel, grid, kStagedThreads + 32, smem, stream, a);
     return grid;
 }
 
@@ -248,9 +267,10 @@ template <typename T, int K, int EPI>
 int launch_one(SpmvArgs<T>& a, const SpmvPlan& plan, cudaStream_t stream) {
     int grid = 0;
     if (plan.path == 0) {
-        a.tile_rows = plan.tile_rows;
+        a.tile_desc = plan.tile_desc;
         a.n_tiles = plan.n_tiles;
         a.stage_elems = plan.stage_elems;
+        a.stage_rows = plan.stage_rows;
         switch (plan.staged_lanes) {
             case 1: grid = launch_staged<T, K, EPI, 1>(a, plan, stream); break;
             case 2: grid = launch_staged<T, K, EPI, 2>(a, plan, stream); break;
@@ -264,12 +284,12 @@ int launch_one(SpmvArgs<T>& a, const SpmvPlan& plan, cudaStream_t stream) {
         if (EPI == EPI_NORM) grid = std::min(grid, kMaxNormBlocks);
         if (g_dry_run) return grid;
         switch (plan.lanes) {
-            case 1: spmv_direct_kernel<T, K, EPI, 1><<<grid, kDirectThreads, 0, stream>>>(a); break;
-            case 2: spmv_direct_kernel<T, K, EPI, 2><<<grid, kDirectThreads, 0, stream>>>(a); break;
-            case 4: spmv_direct_kernel<T, K, EPI, 4><<<grid, kDirectThreads, 0, stream>>>(a); break;
-            case 8: spmv_direct_kernel<T, K, EPI, 8><<<grid, kDirectThreads, 0, stream>>>(a); break;
-            case 16: spmv_direct_kernel<T, K, EPI, 16><<<grid, kDirectThreads, 0, stream>>>(a); break;
-            default: spmv_direct_kernel<T, K, EPI, 32><<<grid, kDirectThreads, 0, stream>>>(a); break;
+            case 1: launch_pdl(spmv_direct_kernel<T, K, EPI, 1>, grid, kDirectThreads, 0, stream, a); break;
+            case 2: launch_pdl(spmv_direct_kernel<T, K, EPI, 2>, grid, kDirectThreads, 0, stream, a); break;
+            case 4: launch_pdl(spmv_direct_kernel<T, K, EPI, 4>, grid, kDirectThreads, 0, stream, a); break;
+            case 8: launch_pdl(spmv_direct_kernel<T, K, EPI, 8>, grid, kDirectThreads, 0, stream, a); break;
+            case 16: launch_pdl(spmv_direct_kernel<T, K, EPI, 16>, grid, kDirectThreads, 0, stream, a); break;
+            default: launch_pdl(spmv_direct_kernel<T, K, EPI, 32>, grid, kDirectThreads, 0, stream, a); break;
         }
     }
     GMG_CUDA(cudaGetLastError());
@@ -291,6 +311,7 @@ int launch_k(int epi, SpmvArgs<T>& a, const SpmvPlan& plan, cudaStream_t stream)
 }  // namespace
 
 void set_launch_dry_run(bool on) { g_dry_run = on; }
+void set_launch_pdl(bool on) { g_use_pdl = on; }
 
 template <typename T>
 int launch_spmv(int epi, int K, SpmvArgs<T> args, const SpmvPlan& plan, cudaStream_t stream) {

@@ -58,14 +58,15 @@ struct SpmvArgs {
     T omega = T(0);
     const T* omega_ptr = nullptr;      // device-resident damping of this sweep (overrides omega)
     double* partials = nullptr;        // NORM: [gridDim.x][2*K]
-    const int* tile_rows = nullptr;    // staged: n_tiles + 1 row offsets
+    const int4* tile_desc = nullptr;   // staged: per tile {first row, end row, first entry & ~3, (end entry + 3) & ~3}
     int n_tiles = 0;
     int stage_elems = 0;               // staged: capacity of one stage in entries (multiple of 4)
+    int stage_rows = 0;                // staged: rows per tile (consumer threads / LANES)
     const CycleControl* ctl = nullptr; // optional early-out
 };
 
 constexpr int kStagedThreads = 256;
-constexpr int kStagedStages = 3;
+constexpr int kStagedStages = 2;
 constexpr int kDirectThreads = 256;
 
 template <int NV, int TPB>
@@ -151,99 +152,145 @@ __device__ __forceinline__ void row_epilogue(const SpmvArgs<T>& a, int row, cons
 }
 
 // ---------------------------------------------------------------------------- staged path
-template <typename T, int K, int EPI, int LANES>
-__global__ void __launch_bounds__(kStagedThreads) spmv_staged_kernel(const SpmvArgs<T> a) {
-    constexpr int TPB = kStagedThreads;
-    constexpr int STAGES = kStagedStages;
-    if (a.ctl && a.ctl->done) return;
+// Shared memory of one stage (all offsets multiples of 16 bytes):
+//   int4   desc      {first row, end row, first entry (aligned down to 4), unused}
+//   int    rowptr[stage_rows + 8]   the tile's slice of rowptr, from row (first row & ~3)
+//   T      vals[stage_elems]
+//   int    colidx[stage_elems]
+// Warp 0 is the producer: one lane waits for a stage to drain (empty barrier), writes the
+// descriptor and issues three bulk copies that complete on the stage's full barrier. Warps
+// 1..8 consume: they never block on each other, only on the stage they need, so a fast warp
+// runs up to STAGES tiles ahead of a slow one.
+__host__ __device__ inline size_t staged_stage_bytes(int stage_rows, int stage_elems, size_t value_size) {
+    return 16 + (size_t)(stage_rows + 8) * sizeof(int) + (size_t)stage_elems * (value_size + sizeof(int));
+}
+
+template <typename T, int K, int EPI, int LANES, int TPB = kStagedThreads, int STAGES = kStagedStages>
+__global__ void __launch_bounds__(TPB + 32) spmv_staged_kernel(const SpmvArgs<T> a) {
+    // TPB consumer threads + one producer warp; STAGES-deep ring
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // first 128 bytes
-    const size_t stage_bytes = (size_t)a.stage_elems * (sizeof(T) + sizeof(int));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // first 128 bytes: 2 * STAGES barriers
+    uint64_t* empty = full + STAGES;
+    const size_t stage_bytes = staged_stage_bytes(a.stage_rows, a.stage_elems, sizeof(T));
     unsigned char* stage0 = smem_raw + 128;
 
     const int tid = threadIdx.x;
-    const int lane = tid % LANES;
     const int n_my = (int)blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], TPB / 32);
+        }
         mbar_init_fence();
     }
     __syncthreads();
-
-    auto issue = [&](int it) {
-        const int tile = blockIdx.x + it * gridDim.x;
-        const int s = it % STAGES;
-        const int p0 = a.rowptr[a.tile_rows[tile]] & ~3;
-        const int p1 = (a.rowptr[a.tile_rows[tile + 1]] + 3) & ~3;
-        const uint32_t cnt = (uint32_t)(p1 - p0);
-        unsigned char* sv = stage0 + s * stage_bytes;
-        unsigned char* sc = sv + (size_t)a.stage_elems * sizeof(T);
-        mbar_arrive_expect_tx(&bars[s], cnt * (uint32_t)(sizeof(T) + sizeof(int)));
-        if (cnt) {
-            bulk_copy_g2s(sv, a.vals + p0, cnt * (uint32_t)sizeof(T), &bars[s]);
-            bulk_copy_g2s(sc, a.colidx + p0, cnt * (uint32_t)sizeof(int), &bars[s]);
-        }
-    };
-    if (tid == 0)
-        for (int it = 0; it < STAGES && it < n_my; ++it) issue(it);
 
     double nrm[2 * K];
 #pragma unroll
     for (int j = 0; j < 2 * K; ++j) nrm[j] = 0.0;
 
-    for (int it = 0; it < n_my; ++it) {
-        const int tile = blockIdx.x + it * gridDim.x;
-        const int s = it % STAGES;
-        const int r0 = a.tile_rows[tile];
-        const int r1 = a.tile_rows[tile + 1];
-        const int base = a.rowptr[r0] & ~3;
-        const int row = r0 + tid / LANES;
-        const bool active = row < r1;
-        int ps = 0, pe = 0;
-        RowOperands<T, K> ops;
-        if (active) {
-            ps = a.rowptr[row] - base;
-            pe = a.rowptr[row + 1] - base;
-            if (lane == 0) load_row_operands<T, K, EPI>(a, row, ops);
-        }
-        const T* sv = reinterpret_cast<const T*>(stage0 + s * stage_bytes);
-        const int* sc = reinterpret_cast<const int*>(stage0 + s * stage_bytes + (size_t)a.stage_elems * sizeof(T));
-
-        mbar_wait(&bars[s], (uint32_t)((it / STAGES) & 1));
-
-        T acc[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = T(0);
-#pragma unroll 4
-        for (int p = ps + lane; p < pe; p += LANES) {
-            const int c = sc[p];
-            const T v = sv[p];
-            const T* xp = a.x + (size_t)c * a.ld;
-#pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] += v * __ldg(xp + k);
-        }
-        if (LANES > 1) {
-#pragma unroll
-            for (int o = LANES / 2; o > 0; o >>= 1) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    if (tid < 32) {
+        // ------------------------------------------------------------------ producer warp
+        // The operator (rowptr, colidx, vals) is constant while a solve runs, so its slabs are
+        // requested right away: under programmatic dependent launch this CTA may start while the
+        // previous kernel in the stream is still draining, and the copies overlap that tail.
+        // Lane l prefetches the descriptor of tile iteration (32 * block + l); lane 0 issues.
+        for (int it0 = 0; it0 < n_my; it0 += 32) {
+            int4 mine = make_int4(0, 0, 0, 0);
+            if (it0 + tid < n_my) mine = a.tile_desc[blockIdx.x + (it0 + tid) * gridDim.x];
+            const int count = min(32, n_my - it0);
+            for (int j = 0; j < count; ++j) {
+                int4 d;
+                d.x = __shfl_sync(0xffffffffu, mine.x, j);
+                d.y = __shfl_sync(0xffffffffu, mine.y, j);
+                d.z = __shfl_sync(0xffffffffu, mine.z, j);
+                d.w = __shfl_sync(0xffffffffu, mine.w, j);
+                if (tid == 0) {
+                    const int it = it0 + j;
+                    const int s = it % STAGES;
+                    if (it >= STAGES) mbar_wait(&empty[s], (uint32_t)((it / STAGES - 1) & 1));
+                    unsigned char* st = stage0 + s * stage_bytes;
+                    int* rp = reinterpret_cast<int*>(st + 16);
+                    unsigned char* sv = st + 16 + (size_t)(a.stage_rows + 8) * sizeof(int);
+                    unsigned char* sc = sv + (size_t)a.stage_elems * sizeof(T);
+                    *reinterpret_cast<int4*>(st) = d;
+                    const int rp0 = d.x & ~3;
+                    const uint32_t n_rp = (uint32_t)(((d.y + 1 + 3) & ~3) - rp0);
+                    const uint32_t cnt = (uint32_t)(d.w - d.z);
+                    mbar_arrive_expect_tx(&full[s], n_rp * 4u + cnt * (uint32_t)(sizeof(T) + sizeof(int)));
+                    bulk_copy_g2s(rp, a.rowptr + rp0, n_rp * 4u, &full[s]);
+                    if (cnt) {
+                        bulk_copy_g2s(sv, a.vals + d.z, cnt * (uint32_t)sizeof(T), &full[s]);
+                        bulk_copy_g2s(sc, a.colidx + d.z, cnt * (uint32_t)sizeof(int), &full[s]);
+                    }
+                }
+                __syncwarp();
             }
         }
-        if (active && lane == 0) row_epilogue<T, K, EPI>(a, row, acc, ops, nrm);
-        __syncthreads();  // everyone is done reading stage s before it is refilled
-        if (tid == 0 && it + STAGES < n_my) issue(it + STAGES);
+        grid_dependency_wait();  // (only so that this CTA does not retire before its predecessor grid)
+    } else {
+        // ------------------------------------------------------------------ consumers
+        // Vectors (x, b, out of the previous kernel) must not be touched before that kernel is done.
+        grid_dependency_wait();
+        grid_launch_dependents();
+        const int ctid = tid - 32;
+        const int lane = ctid % LANES;
+        for (int it = 0; it < n_my; ++it) {
+            const int s = it % STAGES;
+            const unsigned char* st = stage0 + s * stage_bytes;
+            const int* rp = reinterpret_cast<const int*>(st + 16);
+            const T* sv = reinterpret_cast<const T*>(st + 16 + (size_t)(a.stage_rows + 8) * sizeof(int));
+            const int* sc = reinterpret_cast<const int*>(reinterpret_cast<const unsigned char*>(sv) + (size_t)a.stage_elems * sizeof(T));
+
+            mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
+
+            const int4 d = *reinterpret_cast<const int4*>(st);
+            const int row = d.x + ctid / LANES;
+            const bool active = row < d.y;
+            int ps = 0, pe = 0;
+            RowOperands<T, K> ops;
+            if (active) {
+                const int o = row - (d.x & ~3);
+                ps = rp[o] - d.z;
+                pe = rp[o + 1] - d.z;
+                if (lane == 0) load_row_operands<T, K, EPI>(a, row, ops);
+            }
+            T acc[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = T(0);
+#pragma unroll 8
+            for (int p = ps + lane; p < pe; p += LANES) {
+                const int c = sc[p];
+                const T v = sv[p];
+                const T* xp = a.x + (size_t)c * a.ld;
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] += v * __ldg(xp + k);
+            }
+            // every lane of the warp has read its part of stage s: hand it back to the producer
+            __syncwarp();
+            if ((ctid & 31) == 0) mbar_arrive(&empty[s]);
+            if (LANES > 1) {
+#pragma unroll
+                for (int o = LANES / 2; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+                }
+            }
+            if (active && lane == 0) row_epilogue<T, K, EPI>(a, row, acc, ops, nrm);
+        }
     }
-    if (EPI == EPI_NORM) block_sum_store<2 * K, TPB>(nrm, a.partials + (size_t)blockIdx.x * 2 * K);
+    if (EPI == EPI_NORM) block_sum_store<2 * K, TPB + 32>(nrm, a.partials + (size_t)blockIdx.x * 2 * K);
 }
 
 // ---------------------------------------------------------------------------- direct path
 template <typename T, int K, int EPI, int LANES>
 __global__ void __launch_bounds__(kDirectThreads) spmv_direct_kernel(const SpmvArgs<T> a) {
     constexpr int TPB = kDirectThreads;
-    if (a.ctl && a.ctl->done) return;
+    grid_dependency_wait();
+    grid_launch_dependents();
     const int lane = threadIdx.x % LANES;
     const int rows_per_block = TPB / LANES;
     double nrm[2 * K];

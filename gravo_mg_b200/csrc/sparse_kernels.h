@@ -11,7 +11,8 @@ struct SpmvPlan {
     int staged_lanes = 1;    // staged: threads per row (1, 2, 4, 8); 1 sums in CSR order
     int n_tiles = 0;         // staged
     int stage_elems = 0;     // staged: entries per stage (multiple of 4)
-    const int* tile_rows = nullptr;  // device array n_tiles + 1
+    int stage_rows = 0;      // staged: rows per tile = kStagedThreads / staged_lanes
+    const int4* tile_desc = nullptr;  // device array n_tiles: {first row, end row, first entry & ~3, (end entry + 3) & ~3}
 };
 
 constexpr int kMaxRhsTile = 4;        // kernels are instantiated for K = 1..4 columns per pass
@@ -26,7 +27,7 @@ struct NormChunks {
     int n_blocks[kMaxNormChunks] = {0};
 };
 
-size_t staged_smem_bytes(int stage_elems, size_t value_size);
+size_t staged_smem_bytes(int stage_rows, int stage_elems, size_t value_size);
 size_t staged_smem_limit();  // usable dynamic shared memory per CTA on this device
 
 // Launch acc = A x with epilogue `epi` over K (1..4) columns. Returns the grid size used
@@ -37,6 +38,8 @@ int launch_spmv(int epi, int K, SpmvArgs<T> args, const SpmvPlan& plan, cudaStre
 // While on, launch_spmv does everything except launch (occupancy query, opt-in to large shared
 // memory): lets the one-time attribute calls happen outside of stream capture.
 void set_launch_dry_run(bool on);
+// Programmatic dependent launch of the row-product kernels (on by default; thread-local).
+void set_launch_pdl(bool on);
 
 // Reduce NORM partials and update the loop state: residue, history, iter, done.
 // `cond_handle` != 0 additionally drives a CUDA graph while-node (cudaGraphSetConditional).

@@ -82,7 +82,8 @@ const char* gmg_last_error(gmg_handle h);
  * "smoother", "cheb_alpha", and implementation knobs "use_graph" (0/1), "loop_mode" (0 host loop,
  * 1 device while-graph), "kernel_path" (0 staged TMA, 1 direct), "lanes" (staged kernels: threads
  * per row, 0 = chosen from the row length, 1 = one thread per row, sums in CSR order),
- * "profile" (0/1 per-kernel event timing). */
+ * "pdl" (0/1 programmatic dependent launch of consecutive kernels), "profile" (0/1 per-kernel
+ * event timing). */
 int gmg_set_option(gmg_handle h, const char* key, double value);
 int gmg_get_option(gmg_handle h, const char* key, double* value);
 
