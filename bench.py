@@ -166,6 +166,8 @@ def main():
     ap.add_argument("--sweeps", type=int, default=2, help="pre and post sweeps per level")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--pdl", type=int, default=1)
+    ap.add_argument("--fuse-norm", type=int, default=1)
+    ap.add_argument("--tail-rows", type=int, default=0)
     ap.add_argument("--loop-mode", type=int, default=1)
     ap.add_argument("--kernel-path", type=int, default=0)
     ap.add_argument("--use-graph", type=int, default=1)
@@ -231,6 +233,8 @@ def main():
     b.set_option("use_graph", args.use_graph)
     b.set_option("lanes", args.lanes)
     b.set_option("pdl", args.pdl)
+    b.set_option("fuse_norm", args.fuse_norm)
+    b.set_option("tail_rows", args.tail_rows)
     U = solver.prolongation_matrices
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
@@ -305,7 +309,7 @@ def main():
         b.solve_staged()
     b.set_option("profile", 0)
     jac_ms, jac_launches = b.kernel_profile(0, 0)
-    kinds = {0: "jacobi", 1: "residual", 2: "restrict", 3: "prolong_add", 4: "norm", 5: "coarse_solve"}
+    kinds = {0: "jacobi", 1: "residual", 2: "restrict", 3: "prolong_add", 4: "norm", 5: "coarse_solve", 7: "fused_tail"}
     per_kernel = {}
     for kind, name in kinds.items():
         for lvl in range(len(info)):

@@ -151,6 +151,8 @@ int gmg_set_option(gmg_handle h, const char* key, double value) {
         else if (k == "loop_mode") s.loop_mode = (int)value;
         else if (k == "profile") s.profile = value != 0.0;
         else if (k == "pdl") s.use_pdl = value != 0.0, cycle = true;
+        else if (k == "fuse_norm") s.fuse_norm = value != 0.0, cycle = true;
+        else if (k == "tail_rows") s.tail_rows = (int)value, cycle = true;
         else if (k == "kernel_path") s.kernel_path = (int)value, hierarchy = true;
         else throw std::invalid_argument("unknown option: " + k);
         require(s.params.pre_iters >= 0 && s.params.post_iters >= 0 && s.params.pre_iters <= 16 && s.params.post_iters <= 16, "sweep counts must be 0..16");
@@ -182,6 +184,8 @@ int gmg_get_option(gmg_handle h, const char* key, double* value) {
         else if (k == "loop_mode") *value = s.loop_mode;
         else if (k == "profile") *value = s.profile;
         else if (k == "pdl") *value = s.use_pdl;
+        else if (k == "fuse_norm") *value = s.fuse_norm;
+        else if (k == "tail_rows") *value = s.tail_rows;
         else if (k == "kernel_path") *value = s.kernel_path;
         else throw std::invalid_argument("unknown option: " + k);
     });

@@ -25,6 +25,11 @@ public:
     // x = A^-1 b for K columns stored row-major with leading dimension ld. b and x may alias.
     void solve(const double* b, double* x, int K, int ld, const CycleControl* ctl, cudaStream_t stream);
     int size() const { return n_; }
+    // factor storage for kernels that fuse the solve (tail_kernel.cuh): W = L^-1 (lower), Wt = W^T, scratch y
+    const double* w() const { return W_.ptr; }
+    const double* wt() const { return Wt_.ptr; }
+    double* y() const { return y_.ptr; }
+    int ld() const { return npad_; }
     int launches_per_solve() const { return 2; }
     int launches_per_factor() const { return factor_launches_; }
     size_t bytes_per_solve() const { return (size_t)n_ * (size_t)n_ * sizeof(double); }

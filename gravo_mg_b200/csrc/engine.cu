@@ -11,11 +11,12 @@
 #include "dense_coarse.h"
 #include "solver.h"
 #include "sparse_kernels.h"
+#include "tail_kernel.cuh"
 
 namespace gmg {
 namespace {
 
-enum OpKind { OP_JACOBI = 0, OP_RESIDUAL = 1, OP_RESTRICT = 2, OP_PROLONG = 3, OP_NORM = 4, OP_COARSE = 5, OP_ZERO = 6, OP_KINDS = 7 };
+enum OpKind { OP_JACOBI = 0, OP_RESIDUAL = 1, OP_RESTRICT = 2, OP_PROLONG = 3, OP_NORM = 4, OP_COARSE = 5, OP_ZERO = 6, OP_TAIL = 7, OP_KINDS = 8 };
 constexpr int kMaxLevels = 16;
 
 // CSR matrix on the device. Setup arithmetic (Galerkin products, factorisation) is always
@@ -110,6 +111,8 @@ public:
         GMG_CUDA(cudaMemsetAsync(ctl_.ptr, 0, 2 * sizeof(CycleControl), stream_));
         partials_.ensure(kNormChunkStride * kMaxNormChunks);
         rho_.ensure(kMaxLevels);
+        tail_bar_.ensure(4);
+        GMG_CUDA(cudaMemsetAsync(tail_bar_.ptr, 0, 4 * sizeof(unsigned), stream_));
         weights_.ensure((size_t)kMaxLevels * 2 * kMaxSweeps);
         weights64_.ensure((size_t)kMaxLevels * 2 * kMaxSweeps);
         GMG_CUDA(cudaMallocHost((void**)&ctl_host_, sizeof(CycleControl)));
@@ -202,6 +205,7 @@ public:
         // ---- "cycles" (multigrid_solver.cpp:1411-1417)
         launch_cycle_begin(ctl_.ptr, p.max_iter, p.stopping_criteria, p.tolerance, K_, stream_);
         ++launches;
+        for (const Op& op : prologue_) launches += run_op(op, stream_, 0);
         const bool graph = st_->use_graph && !st_->profile;
         if (graph && st_->loop_mode == 1) {
             if (!while_exec_) build_while_graph();
@@ -613,7 +617,7 @@ private:
 
     // multiGridVCycleGS (multigrid_solver.cpp:1059-1088) at level k. `cur` holds x_k on entry and
     // on exit; `pre_done` sweeps were already applied by the caller (zero-guess shortcut).
-    void push_vcycle(int k, T*& cur, T*& alt, int pre_done) {
+    void push_vcycle(int k, T*& cur, T*& alt, int pre_done, bool fused_top) {
         const gmg_params& p = st_->params;
         const int L = n_levels_;
         Level& f = lv_[k];
@@ -640,6 +644,7 @@ private:
         }
         T* ccur = c.x.ptr;
         T* calt = c.t.ptr;
+        if (k + 1 == tail_level_) tail_begin_ = ops_.size();
         if (next_is_coarsest) {
             Op op;
             op.kind = OP_COARSE, op.level = k + 1;
@@ -650,15 +655,19 @@ private:
                 op.kind = OP_ZERO, op.level = k + 1, op.zero_ptr = c.x.ptr, op.zero_bytes = (size_t)c.n * K_ * sizeof(T);
                 ops_.push_back(op);
             }
-            push_vcycle(k + 1, ccur, calt, next_pre_done);
+            push_vcycle(k + 1, ccur, calt, next_pre_done, false);
         }
+        if (k + 1 == tail_level_) tail_end_ = ops_.size();
         {   // x = x + U eps. On level 0 an odd sweep count is evened out by writing to the other
             // buffer, so a cycle always ends in the buffer it started from (graph replay).
             Op op;
             op.kind = OP_PROLONG, op.level = k, op.epi = EPI_ADD, op.plan = &f.P.plan;
             op.args = base_args(f.P);
             op.args.x = ccur, op.args.xin = cur;
-            const bool flip = (k == 0) && ((p.pre_iters + p.post_iters) % 2 != 0);
+            // swaps of this level: (pre - pre_done) + post sweeps [+ 1 if the prolongation flips].
+            // plain cycle: end where it started (even); fused top level: start in t, end in x (odd)
+            const int sweeps_here = p.pre_iters - pre_done + p.post_iters;
+            const bool flip = (k == 0) && (fused_top ? sweeps_here % 2 == 0 : sweeps_here % 2 != 0);
             op.args.out = flip ? alt : cur;
             ops_.push_back(op);
             if (flip) std::swap(cur, alt);
@@ -669,29 +678,55 @@ private:
     void build_cycle() {
         drop_graphs();
         ops_.clear();
+        prologue_.clear();
+        const gmg_params& p = st_->params;
         T* cur = lv_[0].x.ptr;
         T* alt = lv_[0].t.ptr;
+        // The stopping test of cycle i and the first pre-smoothing sweep of cycle i + 1 both need
+        // b - A x of the same iterate: one kernel does both (EPI_NORMJAC). The sweep is speculative
+        // (written to the other buffer), so the final iterate survives when the loop stops.
+        const bool fused = n_levels_ > 0 && p.pre_iters >= 1 && st_->fuse_norm;
+        // levels small enough to live in L2 and be launch-latency bound run as one persistent
+        // kernel (tail_kernel.cuh); never the finest level, whose streaming kernels are better
+        tail_level_ = -1, tail_begin_ = tail_end_ = 0;
+        for (int k = 1; k <= n_levels_ && st_->tail_rows > 0; ++k)
+            if (lv_[k].n <= st_->tail_rows) {
+                tail_level_ = k;
+                break;
+            }
         if (n_levels_ == 0) {
             // no hierarchy could be built (N <= lower_bound): the reference is undefined here
             // (SURVEY Appendix A.13); the whole system goes to the direct coarse solve.
             Op op;
             op.kind = OP_COARSE, op.level = 0;
             ops_.push_back(op);
+        } else if (!fused) {
+            push_vcycle(0, cur, alt, 0, false);
         } else {
-            push_vcycle(0, cur, alt, 0);
+            // prologue (once per solve): sweep 0 of the first cycle, x (cur) -> alt
+            push_sweeps(0, false, 0, 1, cur, alt);
+            prologue_.push_back(ops_.back());
+            ops_.clear();
+            // every cycle starts from the swept iterate in `cur` (= lv_[0].t) and must end with the
+            // final iterate in lv_[0].x so that the speculative sweep lands in lv_[0].t again
+            push_vcycle(0, cur, alt, 1, true);
         }
+        if (tail_level_ > 0 && tail_end_ > tail_begin_) collapse_tail();
         x_final_ = cur;
         {   // residualCheck(LHS, b, x, stoppingCriteria) (multigrid_solver.cpp:1413)
             Op op;
-            op.kind = OP_NORM, op.level = 0, op.epi = EPI_NORM, op.plan = &lv_[0].A.plan;
+            op.kind = OP_NORM, op.level = 0, op.epi = fused ? EPI_NORMJAC : EPI_NORM, op.plan = &lv_[0].A.plan;
             op.args = base_args(lv_[0].A);
             op.args.x = cur, op.args.b = lv_[0].b.ptr;
+            if (fused) op.args.dinv = lv_[0].dinv.ptr, op.args.omega_ptr = weight_ptr(0, false, 0), op.args.out = alt;
             ops_.push_back(op);
         }
         cycle_dirty_ = false;
         // one-time per-kernel attribute/occupancy calls must not land inside a stream capture
         set_launch_dry_run(true);
         try {
+            for (const Op& op : prologue_)
+                if (op.plan) run_op(op, stream_, 0);
             for (const Op& op : ops_)
                 if (op.plan) run_op(op, stream_, 0);
         } catch (...) {
@@ -701,6 +736,82 @@ private:
         set_launch_dry_run(false);
     }
 
+    int tail_grid() {
+        if (!tail_grid_) {
+            int dev = 0;
+            GMG_CUDA(cudaGetDevice(&dev));
+            GMG_CUDA(cudaDeviceGetAttribute(&tail_grid_, cudaDevAttrMultiProcessorCount, dev));
+        }
+        return tail_grid_;
+    }
+
+    // Replace ops_[tail_begin_, tail_end_) — everything between the restriction into the tail
+    // level and the prolongation out of it — by one OP_TAIL whose operator table is on the device.
+    void collapse_tail() {
+        std::vector<TailOp<T>> table;
+        for (size_t i = tail_begin_; i < tail_end_; ++i) {
+            const Op& op = ops_[i];
+            if (op.kind == OP_ZERO) {
+                TailOp<T> z;
+                z.kind = TAIL_ZERO, z.dst = op.zero_ptr, z.count = op.zero_bytes;
+                table.push_back(z);
+            } else if (op.kind == OP_COARSE) {
+                Level& c = lv_[op.level];
+                const size_t count = (size_t)c.n * K_;
+                const double* b64 = reinterpret_cast<const double*>(c.b.ptr);
+                double* x64 = reinterpret_cast<double*>(c.x.ptr);
+                if (sizeof(T) == 4) {
+                    TailOp<T> cast;
+                    cast.kind = TAIL_TO_F64, cast.src = c.b.ptr, cast.dst = coarse_b64_.ptr, cast.count = count;
+                    table.push_back(cast);
+                    b64 = coarse_b64_.ptr, x64 = coarse_x64_.ptr;
+                }
+                for (int k0 = 0; k0 < K_; k0 += kMaxRhsTile) {
+                    const int kt = std::min(kMaxRhsTile, K_ - k0);
+                    TailOp<T> u;  // y = W b: row i of W is column i of Wt
+                    u.kind = TAIL_COLDOT, u.kcols = kt, u.M = coarse_.wt(), u.ldm = coarse_.ld(), u.n = c.n, u.upper = 1;
+                    u.v = b64 + k0, u.v_ld = K_, u.out = coarse_.y(), u.out_ld = kt;
+                    table.push_back(u);
+                    TailOp<T> l;  // x = W^T y
+                    l.kind = TAIL_COLDOT, l.kcols = kt, l.M = coarse_.w(), l.ldm = coarse_.ld(), l.n = c.n, l.upper = 0;
+                    l.v = coarse_.y(), l.v_ld = kt, l.out = x64 + k0, l.out_ld = K_;
+                    table.push_back(l);
+                }
+                if (sizeof(T) == 4) {
+                    TailOp<T> cast;
+                    cast.kind = TAIL_FROM_F64, cast.src = coarse_x64_.ptr, cast.dst = c.x.ptr, cast.count = count;
+                    table.push_back(cast);
+                }
+            } else {
+                for (int k0 = 0; k0 < K_; k0 += kMaxRhsTile) {
+                    TailOp<T> r;
+                    r.kind = TAIL_ROWS, r.epi = op.epi, r.kcols = std::min(kMaxRhsTile, K_ - k0);
+                    {   // threads per row: as many as fill the grid in one pass, at most the row length
+                        const int threads = tail_grid() * kTailThreads;
+                        int lanes = 1;
+                        while (lanes < 8 && lanes * 2 <= op.plan->lanes && (int64_t)op.args.n_rows * lanes * 2 <= threads) lanes *= 2;
+                        r.lanes = lanes;
+                    }
+                    r.a = op.args;
+                    r.a.x = op.args.x + k0;
+                    if (r.a.b) r.a.b = op.args.b + k0;
+                    if (r.a.xin) r.a.xin = op.args.xin + k0;
+                    r.a.out = op.args.out + k0;
+                    if (r.a.out2) r.a.out2 = op.args.out2 + k0;
+                    table.push_back(r);
+                }
+            }
+        }
+        tail_table_.ensure(table.size() * sizeof(TailOp<T>));
+        GMG_CUDA(cudaMemcpyAsync(tail_table_.ptr, table.data(), table.size() * sizeof(TailOp<T>), cudaMemcpyHostToDevice, stream_));
+        GMG_CUDA(cudaStreamSynchronize(stream_));  // `table` is a local
+        n_tail_ops_ = (int)table.size();
+        Op tail;
+        tail.kind = OP_TAIL, tail.level = tail_level_;
+        ops_.erase(ops_.begin() + tail_begin_, ops_.begin() + tail_end_);
+        ops_.insert(ops_.begin() + tail_begin_, tail);
+    }
+
     int run_op(const Op& op, cudaStream_t s, unsigned long long cond) {
         int launches = 0;
         const gmg_params& p = st_->params;
@@ -708,6 +819,13 @@ private:
             case OP_ZERO:
                 GMG_CUDA(cudaMemsetAsync(op.zero_ptr, 0, op.zero_bytes, s));
                 break;
+            case OP_TAIL: {
+                const int sms = tail_grid();
+                tail_kernel<T><<<sms, kTailThreads, 0, s>>>(reinterpret_cast<const TailOp<T>*>(tail_table_.ptr), n_tail_ops_, tail_bar_.ptr);
+                GMG_CUDA(cudaGetLastError());
+                launches += 1;
+                break;
+            }
             case OP_COARSE: {
                 Level& c = lv_[op.level];
                 if (sizeof(T) == 8) {
@@ -731,7 +849,8 @@ private:
                     a.x = op.args.x + k0, a.b = op.args.b + k0;
                     a.partials = partials_.ptr + (size_t)chunks.n_chunks * kNormChunkStride;
                     chunks.kt[chunks.n_chunks] = kt;
-                    chunks.n_blocks[chunks.n_chunks] = launch_spmv<T>(EPI_NORM, kt, a, *op.plan, s);
+                    if (op.args.out) a.out = op.args.out + k0;
+                    chunks.n_blocks[chunks.n_chunks] = launch_spmv<T>(op.epi, kt, a, *op.plan, s);
                     ++chunks.n_chunks;
                     ++launches;
                 }
@@ -866,7 +985,11 @@ private:
     std::vector<HostCsr> r_host_;
     bool hierarchy_ready_ = false, pattern_ready_ = false, staged_ = false, solved_ = false, cycle_dirty_ = true;
     bool numeric_ready_ = false;
-    std::vector<Op> ops_;
+    std::vector<Op> ops_, prologue_;
+    int tail_level_ = -1, n_tail_ops_ = 0, tail_grid_ = 0;
+    size_t tail_begin_ = 0, tail_end_ = 0;
+    DeviceBuffer<unsigned char> tail_table_;
+    DeviceBuffer<unsigned> tail_bar_;
     T* x_final_ = nullptr;
     int launches_per_cycle_ = 0;
     cudaGraphExec_t cycle_exec_ = nullptr, while_exec_ = nullptr;

@@ -43,6 +43,9 @@ struct SolverState {
     int kernel_path = 0;             // 0 staged (TMA) where it fits, 1 direct everywhere
     int staged_lanes = 0;            // staged kernels: threads per row; 0 = from the mean row length
     bool profile = false;
+    int tail_rows = 0;               // levels with at most this many rows run inside the fused tail kernel; off by
+                                     // default: measured slower than PDL-chained kernels ("Coarse tail")
+    bool fuse_norm = true;           // stopping test fused with the next cycle's first sweep
     bool use_pdl = true;             // programmatic dependent launch of the row-product kernels
     std::map<std::string, double> solver_timing;           // reference solverTiming keys
     std::vector<std::pair<double, double>> convergence;    // (elapsed ms, residue) per cycle

@@ -258,7 +258,7 @@ int launch_staged(SpmvArgs<T>& a, const SpmvPlan& plan, cudaStream_t stream) {
     auto kernel = spmv_staged_kernel<T, K, EPI, LANES>;
     const int per_sm = resident_blocks((const void*)kernel, kStagedThreads + 32, smem);
     int grid = std::min(std::max(plan.n_tiles, 1), per_sm * num_sms());
-    if (EPI == EPI_NORM) grid = std::min(grid, kMaxNormBlocks);
+    if (EPI == EPI_NORM || EPI == EPI_NORMJAC) grid = std::min(grid, kMaxNormBlocks);
     if (!g_dry_run) launch_pdl(kernel, grid, kStagedThreads + 32, smem, stream, a);
     return grid;
 }
@@ -281,7 +281,7 @@ int launch_one(SpmvArgs<T>& a, const SpmvPlan& plan, cudaStream_t stream) {
         const int rows_per_block = kDirectThreads / plan.lanes;
         const int64_t want = ((int64_t)a.n_rows + rows_per_block - 1) / rows_per_block;
         grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)num_sms() * 32);
-        if (EPI == EPI_NORM) grid = std::min(grid, kMaxNormBlocks);
+        if (EPI == EPI_NORM || EPI == EPI_NORMJAC) grid = std::min(grid, kMaxNormBlocks);
         if (g_dry_run) return grid;
         switch (plan.lanes) {
             case 1: launch_pdl(spmv_direct_kernel<T, K, EPI, 1>, grid, kDirectThreads, 0, stream, a); break;
@@ -304,6 +304,7 @@ int launch_k(int epi, SpmvArgs<T>& a, const SpmvPlan& plan, cudaStream_t stream)
         case EPI_RESIDUAL: return launch_one<T, K, EPI_RESIDUAL>(a, plan, stream);
         case EPI_ADD: return launch_one<T, K, EPI_ADD>(a, plan, stream);
         case EPI_NORM: return launch_one<T, K, EPI_NORM>(a, plan, stream);
+        case EPI_NORMJAC: return launch_one<T, K, EPI_NORMJAC>(a, plan, stream);
     }
     throw std::invalid_argument("unknown epilogue");
 }

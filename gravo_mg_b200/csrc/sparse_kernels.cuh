@@ -9,6 +9,8 @@
 //   EPI_RESIDUAL  out_i = b_i - acc_i                                   (:1066)
 //   EPI_ADD       out_i = xin_i + acc_i                                 x += U e (:1082)
 //   EPI_NORM      partial sums of w_i (acc_i - b_i)^2 and w_i b_i^2     residualCheck (:1228-1277)
+//   EPI_NORMJAC   EPI_NORM and EPI_JACOBI from the same row product: the stopping test of one
+//                 cycle and the first pre-smoothing sweep of the next both need b - A x
 //
 // Two data paths:
 //   staged  persistent CTAs walk row tiles; the tile's contiguous (colidx, vals) slab is
@@ -26,7 +28,7 @@
 
 namespace gmg {
 
-enum Epilogue { EPI_SPMV = 0, EPI_JACOBI = 1, EPI_RESIDUAL = 2, EPI_ADD = 3, EPI_NORM = 4 };
+enum Epilogue { EPI_SPMV = 0, EPI_JACOBI = 1, EPI_RESIDUAL = 2, EPI_ADD = 3, EPI_NORM = 4, EPI_NORMJAC = 5 };
 
 // Device-resident loop state of one solve (multigrid_solver.cpp:1411-1417).
 struct CycleControl {
@@ -101,15 +103,15 @@ struct RowOperands {
 template <typename T, int K, int EPI>
 __device__ __forceinline__ void load_row_operands(const SpmvArgs<T>& a, int row, RowOperands<T, K>& r) {
     const size_t o = (size_t)row * a.ld;
-    if (EPI == EPI_JACOBI || (EPI == EPI_SPMV && a.out2)) {
+    if (EPI == EPI_JACOBI || EPI == EPI_NORMJAC || (EPI == EPI_SPMV && a.out2)) {
         const T om = a.omega_ptr ? *a.omega_ptr : a.omega;
         r.scale = om * a.dinv[row];
     }
-    if (EPI == EPI_JACOBI || EPI == EPI_RESIDUAL || EPI == EPI_NORM) {
+    if (EPI == EPI_JACOBI || EPI == EPI_RESIDUAL || EPI == EPI_NORM || EPI == EPI_NORMJAC) {
 #pragma unroll
         for (int k = 0; k < K; ++k) r.b[k] = a.b[o + k];
     }
-    if (EPI == EPI_JACOBI) {
+    if (EPI == EPI_JACOBI || EPI == EPI_NORMJAC) {
 #pragma unroll
         for (int k = 0; k < K; ++k) r.xo[k] = a.x[o + k];
     }
@@ -117,7 +119,7 @@ __device__ __forceinline__ void load_row_operands(const SpmvArgs<T>& a, int row,
 #pragma unroll
         for (int k = 0; k < K; ++k) r.xo[k] = a.xin[o + k];
     }
-    if (EPI == EPI_NORM) r.w = a.weight ? a.weight[row] : 1.0;
+    if (EPI == EPI_NORM || EPI == EPI_NORMJAC) r.w = a.weight ? a.weight[row] : 1.0;
 }
 
 template <typename T, int K, int EPI>
@@ -140,13 +142,17 @@ __device__ __forceinline__ void row_epilogue(const SpmvArgs<T>& a, int row, cons
     } else if (EPI == EPI_ADD) {
 #pragma unroll
         for (int k = 0; k < K; ++k) a.out[o + k] = r.xo[k] + acc[k];
-    } else {  // EPI_NORM
+    } else {  // EPI_NORM, EPI_NORMJAC
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const double bk = (double)r.b[k];
             const double d = (double)acc[k] - bk;
             nrm[2 * k] += r.w * d * d;
             nrm[2 * k + 1] += r.w * bk * bk;
+        }
+        if (EPI == EPI_NORMJAC) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) a.out[o + k] = r.xo[k] + r.scale * (r.b[k] - acc[k]);
         }
     }
 }
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(TPB + 32) spmv_staged_kernel(const SpmvArgs<T>
             if (active && lane == 0) row_epilogue<T, K, EPI>(a, row, acc, ops, nrm);
         }
     }
-    if (EPI == EPI_NORM) block_sum_store<2 * K, TPB + 32>(nrm, a.partials + (size_t)blockIdx.x * 2 * K);
+    if (EPI == EPI_NORM || EPI == EPI_NORMJAC) block_sum_store<2 * K, TPB + 32>(nrm, a.partials + (size_t)blockIdx.x * 2 * K);
 }
 
 // ---------------------------------------------------------------------------- direct path
@@ -325,7 +331,7 @@ __global__ void __launch_bounds__(kDirectThreads) spmv_direct_kernel(const SpmvA
             row_epilogue<T, K, EPI>(a, row, acc, ops, nrm);
         }
     }
-    if (EPI == EPI_NORM) block_sum_store<2 * K, TPB>(nrm, a.partials + (size_t)blockIdx.x * 2 * K);
+    if (EPI == EPI_NORM || EPI == EPI_NORMJAC) block_sum_store<2 * K, TPB>(nrm, a.partials + (size_t)blockIdx.x * 2 * K);
 }
 
 }  // namespace gmg

@@ -82,7 +82,9 @@ const char* gmg_last_error(gmg_handle h);
  * "smoother", "cheb_alpha", and implementation knobs "use_graph" (0/1), "loop_mode" (0 host loop,
  * 1 device while-graph), "kernel_path" (0 staged TMA, 1 direct), "lanes" (staged kernels: threads
  * per row, 0 = chosen from the row length, 1 = one thread per row, sums in CSR order),
- * "pdl" (0/1 programmatic dependent launch of consecutive kernels), "profile" (0/1 per-kernel
+ * "pdl" (0/1 programmatic dependent launch of consecutive kernels), "fuse_norm" (0/1 stopping
+ * test and next cycle's first sweep in one kernel), "tail_rows" (levels with at most this many
+ * rows run inside one persistent kernel with grid barriers; 0 = one kernel per operator), "profile" (0/1 per-kernel
  * event timing). */
 int gmg_set_option(gmg_handle h, const char* key, double value);
 int gmg_get_option(gmg_handle h, const char* key, double* value);
@@ -151,7 +153,8 @@ int gmg_get_level_matrix(gmg_handle h, int32_t level, int32_t* indptr, int32_t* 
 int gmg_level_op(gmg_handle h, int32_t kind, int32_t level, const double* a, const double* b, double* out,
                  int32_t sweeps);
 /* Per-kernel device time accumulated while option "profile" = 1. Kernel kinds:
- * 0 jacobi, 1 residual, 2 restrict, 3 prolong_add, 4 norm, 5 coarse_solve. Level -1 sums levels. */
+ * 0 jacobi, 1 residual, 2 restrict, 3 prolong_add, 4 norm, 5 coarse_solve, 7 fused coarse tail
+ * (filed under its first level). Level -1 sums levels. */
 int gmg_kernel_profile(gmg_handle h, int32_t kind, int32_t level, double* total_ms, int64_t* launches);
 int gmg_reset_kernel_profile(gmg_handle h);
 /* Number of kernel launches issued (or replayed through graphs) by the last solve. */

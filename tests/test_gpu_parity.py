@@ -311,6 +311,23 @@ def test_launch_modes_give_identical_results(ico10k):
         assert it == results[0][1] and res == results[0][2]
 
 
+def test_fused_coarse_tail_matches_per_operator_kernels(ico10k, torus_mid):
+    """Option tail_rows: levels below the threshold run inside one persistent kernel with grid
+    barriers; same arithmetic up to the lane split of the row sums."""
+    for p in (ico10k, torus_mid):
+        xs = []
+        for tail in (0, 100000):
+            solver = p.new_solver(tolerance=1e-6)
+            solver.solver.set_option("tail_rows", tail)
+            xs.append(solver.solve(p.lhs, p.rhs))
+            iters = solver.solver_timing["iterations"]
+        bound = 50 * EPS * abs(p.lhs).sum(0).max() * np.linalg.norm(xs[0])
+        assert np.linalg.norm(p.lhs @ (xs[0] - xs[1])) <= bound
+        o = _jacobi_oracle(p, solver, tolerance=1e-6)
+        o.solve(p.lhs, p.rhs)
+        assert abs(int(o.solver_timing["iterations"]) - int(iters)) <= 1
+
+
 def test_kernel_paths_agree(ico10k):
     p = ico10k
     xs = []
