@@ -252,6 +252,58 @@ class MultigridSolver:
             for t, r in self.convergence():
                 f.write(f"{_fmt(t)},{_fmt(r)}\n")
 
+    # ------------------------------------------------------------------ multi-GPU (one process per GPU)
+    def dist_configure(self, rank, world, replicate_rows=-1):
+        """Row-range layout for ``world`` ranks (host-only; call before staging)."""
+        check(self._h, lib.gmg_dist_configure(self._h, int(rank), int(world), int(replicate_rows)))
+        self._dist = (int(rank), int(world))
+
+    def distribute(self, replicate_rows=-1):
+        """Join the NCCL communicator of the default torch.distributed process group: rank 0
+        creates the NCCL unique id, torch.distributed broadcasts its bytes (the plumbing), every
+        rank then calls ncclCommInitRank through the C ABI. After this every rank must make the
+        same solve calls with the same global inputs."""
+        import torch
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        self.dist_configure(rank, world, replicate_rows)
+        if world == 1:
+            return
+        buf = (C.c_ubyte * 256)()
+        size = C.c_int64(0)
+        if rank == 0:
+            check(None, lib.gmg_dist_unique_id(buf, 256, C.byref(size)))
+        on_gpu = dist.get_backend() == "nccl"
+        t = torch.tensor([size.value] + list(buf), dtype=torch.int64, device="cuda" if on_gpu else "cpu")
+        dist.broadcast(t, src=0)
+        vals = t.cpu().tolist()
+        n = int(vals[0])
+        raw = (C.c_ubyte * 256)(*[int(v) for v in vals[1:]])
+        check(self._h, lib.gmg_dist_init(self._h, raw, n))
+
+    def dist_layout(self, lhs):
+        """Host-only: compute ranges and halo lists for the pattern of ``lhs`` (tests, inspection)."""
+        ap, ai, _ = _csr_arrays(lhs, self._n)
+        check(self._h, lib.gmg_dist_layout(self._h, self._n, i32(ap), i32(ai)))
+
+    def dist_ranges(self, level):
+        world = getattr(self, "_dist", (0, 1))[1]
+        out = np.zeros(world + 1, dtype=np.int64)
+        rep = C.c_int32()
+        check(self._h, lib.gmg_dist_ranges(self._h, int(level), out.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(rep)))
+        return out, bool(rep.value)
+
+    def dist_halo(self, op, level, peer):
+        """(send, recv) global index lists of operator ``op`` ('A', 'R', 'P') towards ``peer``."""
+        op = {"A": 0, "R": 1, "P": 2}[op] if isinstance(op, str) else int(op)
+        ns, nr = C.c_int64(0), C.c_int64(0)
+        check(self._h, lib.gmg_dist_halo(self._h, op, int(level), int(peer), None, C.byref(ns), None, C.byref(nr)))
+        send = np.empty(ns.value, dtype=np.int32)
+        recv = np.empty(nr.value, dtype=np.int32)
+        check(self._h, lib.gmg_dist_halo(self._h, op, int(level), int(peer), i32(send), C.byref(ns), i32(recv), C.byref(nr)))
+        return send, recv
+
     # ------------------------------------------------------------------ options / measurement
     def set_option(self, key, value):
         check(self._h, lib.gmg_set_option(self._h, key.encode(), float(value)))

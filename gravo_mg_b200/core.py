@@ -116,6 +116,12 @@ class MultigridSolver(object):
     def residual(self, lhs, rhs, solution, type=2):
         return self.solver.residual(lhs, rhs, solution, type)
 
+    def distribute(self, replicate_rows=-1):
+        """Multi-GPU (addition): shard the V-cycle over the ranks of the default torch.distributed
+        process group, one process per GPU. Every rank must then call ``solve`` with the same
+        global ``lhs`` / ``rhs`` and gets the full solution back."""
+        self.solver.distribute(replicate_rows)
+
     # Additions: the maps the CSV writers dump, as Python objects.
     @property
     def hierarchy_timing(self):

@@ -8,6 +8,7 @@
 #include <stdexcept>
 #include <string>
 
+#include "nccl_dl.h"
 #include "solver.h"
 
 using gmg::SolverState;
@@ -311,6 +312,82 @@ int gmg_residual(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t
     return guarded(h, [&] {
         require(a_indptr && a_indices && a_data && rhs && x && out, "null argument");
         *out = engine(h).residual(n, a_indptr, a_indices, a_data, rhs, x, K, type);
+    });
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------
+int gmg_dist_configure(gmg_handle h, int32_t rank, int32_t world, int64_t replicate_rows) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(world >= 1 && rank >= 0 && rank < world, "rank must be in [0, world)");
+        SolverState& s = h->s;
+        s.dist = gmg::DistLayout();
+        s.dist.rank = rank, s.dist.world = world;
+        if (replicate_rows >= 0) s.replicate_rows = replicate_rows;
+        if (s.engine) s.engine->invalidate_hierarchy();
+    });
+}
+
+int gmg_dist_unique_id(void* id_out, int64_t capacity, int64_t* size) {
+    return guarded(nullptr, [&] {
+        require(id_out && size, "null argument");
+        require(capacity >= (int64_t)sizeof(ncclUniqueId), "buffer too small for an NCCL unique id");
+        ncclUniqueId id;
+        GMG_NCCL(gmg::nccl().GetUniqueId(&id));
+        std::memcpy(id_out, &id, sizeof id);
+        *size = (int64_t)sizeof id;
+    });
+}
+
+int gmg_dist_init(gmg_handle h, const void* id, int64_t size) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(id && size == (int64_t)sizeof(ncclUniqueId), "expected the bytes of an NCCL unique id");
+        engine(h).dist_init(id);
+    });
+}
+
+int gmg_dist_layout(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t* a_indices) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(a_indptr && a_indices, "null argument");
+        require(n == h->s.n, "lhs has a different number of rows than the point set of the constructor");
+        gmg::compute_level_patterns(h->s, n, a_indptr, a_indices);
+        gmg::compute_dist_layout(h->s);
+    });
+}
+
+int gmg_dist_ranges(gmg_handle h, int32_t level, int64_t* ranges, int32_t* replicated) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        const gmg::DistLayout& d = h->s.dist;
+        require(level >= 0 && level < (int)d.ranges.size(), "level out of range (call gmg_dist_layout or stage a system first)");
+        require(ranges && replicated, "null argument");
+        std::copy(d.ranges[level].begin(), d.ranges[level].end(), ranges);
+        *replicated = d.sharded(level) ? 0 : 1;
+    });
+}
+
+int gmg_dist_halo(gmg_handle h, int32_t op, int32_t level, int32_t peer, int32_t* send, int64_t* n_send, int32_t* recv,
+                  int64_t* n_recv) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        const gmg::DistLayout& d = h->s.dist;
+        require(op >= 0 && op < 3 && n_send && n_recv, "bad argument");
+        require(level >= 0 && level < (int)d.halo[op].size() && peer >= 0 && peer < d.world, "level or peer out of range");
+        const gmg::HaloLists& hl = d.halo[op][level];
+        static const std::vector<int> none;
+        const std::vector<int>& s = hl.send.empty() ? none : hl.send[peer];
+        const std::vector<int>& r = hl.recv.empty() ? none : hl.recv[peer];
+        if (send) {
+            require(*n_send >= (int64_t)s.size(), "send buffer too small");
+            std::copy(s.begin(), s.end(), send);
+        }
+        if (recv) {
+            require(*n_recv >= (int64_t)r.size(), "recv buffer too small");
+            std::copy(r.begin(), r.end(), recv);
+        }
+        *n_send = (int64_t)s.size(), *n_recv = (int64_t)r.size();
     });
 }
 

@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "dense_coarse.h"
+#include "nccl_dl.h"
 #include "solver.h"
 #include "sparse_kernels.h"
 #include "tail_kernel.cuh"
@@ -16,7 +17,7 @@
 namespace gmg {
 namespace {
 
-enum OpKind { OP_JACOBI = 0, OP_RESIDUAL = 1, OP_RESTRICT = 2, OP_PROLONG = 3, OP_NORM = 4, OP_COARSE = 5, OP_ZERO = 6, OP_TAIL = 7, OP_KINDS = 8 };
+enum OpKind { OP_JACOBI = 0, OP_RESIDUAL = 1, OP_RESTRICT = 2, OP_PROLONG = 3, OP_NORM = 4, OP_COARSE = 5, OP_ZERO = 6, OP_TAIL = 7, OP_HALO = 8, OP_ALLGATHER = 9, OP_KINDS = 10 };
 constexpr int kMaxLevels = 16;
 
 // CSR matrix on the device. Setup arithmetic (Galerkin products, factorisation) is always
@@ -54,14 +55,17 @@ struct DevMat {
         launch_expand_rows(rows, indptr.ptr, rowidx.ptr, s);
     }
     // Choose the kernel path and build the row tiles for the staged one.
-    void make_plan(const std::vector<int>& indptr_h, int prefer_path, int staged_lanes, cudaStream_t s) {
+    void make_plan(const std::vector<int>& indptr_h, int prefer_path, int staged_lanes, cudaStream_t s, int row_begin = 0,
+                   int row_end = -1) {
+        if (row_end < 0) row_end = rows;
         const double avg = rows ? (double)nnz / rows : 0.0;
         int lanes = 1;
         while (lanes < 32 && lanes < avg) lanes *= 2;
         plan = SpmvPlan();
         plan.lanes = lanes;
         plan.path = 1;
-        if (prefer_path == 0 && rows > 0) {
+        plan.row_begin = row_begin, plan.row_end = row_end;
+        if (prefer_path == 0 && row_end > row_begin) {
             // threads per row of the staged kernel: enough rows per tile to keep the CTA busy, few
             // enough entries per tile that many CTAs fit one SM's shared memory
             int sl = staged_lanes;
@@ -71,7 +75,7 @@ struct DevMat {
             const size_t per_stage = (staged_smem_limit() / 2 - 1280) / kStagedStages - 16 - (size_t)(stage_rows + 8) * sizeof(int);
             const int cap = (int)(per_stage / (sizeof(T) + sizeof(int))) & ~3;
             int worst = 0;
-            std::vector<int> t = plan_row_tiles(indptr_h, stage_rows, cap, &worst);
+            std::vector<int> t = plan_row_tiles(indptr_h, stage_rows, cap, &worst, row_begin, row_end);
             if (worst <= cap) {
                 std::vector<int4> desc(t.size() - 1);
                 for (size_t i = 0; i + 1 < t.size(); ++i)
@@ -126,6 +130,7 @@ public:
     ~Engine() override {
         cudaSetDevice(st_->params.device);
         drop_graphs();
+        if (comm_) nccl().CommDestroy(comm_);
         for (auto& e : ev_) cudaEventDestroy(e);
         for (auto& e : prof_events_) cudaEventDestroy(e);
         if (ctl_host_) cudaFreeHost(ctl_host_);
@@ -150,10 +155,11 @@ public:
         if (K < 1 || K > kMaxRhsTile * kMaxNormChunks) throw std::invalid_argument("number of right-hand sides must be 1..32");
         if (indptr[0] != 0) throw std::invalid_argument("lhs indptr must start at 0");
         const int64_t nnz = indptr[n];
-        if (!hierarchy_ready_) upload_hierarchy();
-        const bool same = pattern_ready_ && (int64_t)a_indptr_h_.size() == n + 1 && (int64_t)a_indices_h_.size() == nnz &&
-                          std::memcmp(a_indptr_h_.data(), indptr, (n + 1) * sizeof(int)) == 0 &&
-                          std::memcmp(a_indices_h_.data(), indices, nnz * sizeof(int)) == 0;
+        if (!hierarchy_ready_) pattern_ready_ = false;
+        const bool same = pattern_ready_ && !st_->a_pat.empty() && st_->a_pat[0].rows == n &&
+                          (int64_t)st_->a_pat[0].indices.size() == nnz &&
+                          std::memcmp(st_->a_pat[0].indptr.data(), indptr, (n + 1) * sizeof(int)) == 0 &&
+                          std::memcmp(st_->a_pat[0].indices.data(), indices, nnz * sizeof(int)) == 0;
         if (!same) setup_pattern(n, indptr, indices);
         lv_[0].A.upload_values(data, stream_);
         numeric_ready_ = false;
@@ -171,6 +177,7 @@ public:
         GMG_CUDA(cudaSetDevice(st_->params.device));
         if (!solved_) throw std::logic_error("fetch_solution before solve_staged");
         const size_t count = (size_t)st_->n * K_;
+        if (st_->dist.sharded(0)) allgather_rows(0, x_final_, stream_);
         if (sizeof(T) == 4) launch_cast_f32_f64(reinterpret_cast<const float*>(x_final_), x64_.ptr, count, stream_);
         const double* src = sizeof(T) == 4 ? x64_.ptr : reinterpret_cast<const double*>(x_final_);
         GMG_CUDA(cudaMemcpyAsync(x_out, src, count * sizeof(double), cudaMemcpyDeviceToHost, stream_));
@@ -206,7 +213,7 @@ public:
         launch_cycle_begin(ctl_.ptr, p.max_iter, p.stopping_criteria, p.tolerance, K_, stream_);
         ++launches;
         for (const Op& op : prologue_) launches += run_op(op, stream_, 0);
-        const bool graph = st_->use_graph && !st_->profile;
+        const bool graph = st_->use_graph && !st_->profile && st_->dist.world <= 1;  // NCCL exchanges are issued from the host
         if (graph && st_->loop_mode == 1) {
             if (!while_exec_) build_while_graph();
             GMG_CUDA(cudaGraphLaunch(while_exec_, stream_));
@@ -360,6 +367,7 @@ public:
     void level_op(int kind, int level, const double* a, const double* b, double* out, int sweeps) override {
         GMG_CUDA(cudaSetDevice(st_->params.device));
         if (!staged_) throw std::logic_error("level_op before stage_system");
+        if (st_->dist.world > 1) throw std::logic_error("level_op is a single-GPU test entry point");
         set_launch_pdl(st_->use_pdl);
         const int L = n_levels_;
         if (level < 0 || level > L) throw std::invalid_argument("level out of range");
@@ -502,65 +510,144 @@ private:
         const SpmvPlan* plan = nullptr;
         void* zero_ptr = nullptr;
         size_t zero_bytes = 0;
+        int halo_op = 0;          // OP_HALO: HALO_A / HALO_R / HALO_P of `level`
+        T* vec = nullptr;         // OP_HALO / OP_ALLGATHER: the vector
+        T* vec2 = nullptr;        // OP_ALLGATHER: optional second vector of the same level
     };
 
     // ---- setup -------------------------------------------------------------------------
-    void upload_hierarchy() {
+    // Symbolic phase, once per hierarchy and sparsity pattern of the lhs (host work in
+    // compute_level_patterns / compute_dist_layout, solver.h): upload U, R = U^T and the patterns
+    // of A_k U_k and of every Galerkin operator, build the row-tile plans for this rank's row
+    // ranges, the halo index lists and the coarse workspace.
+    void setup_pattern(int64_t n, const int* indptr, const int* indices) {
         const auto& U = st_->hier.U;
         n_levels_ = (int)U.size();
         if (n_levels_ + 1 > kMaxLevels) throw std::invalid_argument("too many levels");
+        if (!hierarchy_ready_) st_->r_host.clear();
+        compute_level_patterns(*st_, n, indptr, indices);
+        compute_dist_layout(*st_);
+        const DistLayout& d = st_->dist;
+        if (d.world > 1 && !comm_) throw std::logic_error("multi-GPU layout configured but gmg_dist_init has not been called");
+        auto range = [&](int level, bool sharded, int& b, int& e) {
+            b = sharded ? (int)d.begin(level) : 0;
+            e = sharded ? (int)d.end(level) : -1;
+        };
         lv_.clear();
         lv_.resize(n_levels_ + 1);
         lv_[0].n = (int)st_->n;
-        r_host_.clear();
+        for (int k = 0; k < n_levels_; ++k) lv_[k + 1].n = (int)U[k].cols;
+        int b = 0, e = -1;
         for (int k = 0; k < n_levels_; ++k) {
             const HostCsr& u = U[k];
-            if (u.rows != lv_[k].n) throw std::invalid_argument("prolongation matrix has the wrong number of rows for its level");
-            lv_[k + 1].n = (int)u.cols;
+            const HostCsr& r = st_->r_host[k];
             lv_[k].P.upload_pattern(u, stream_);
             lv_[k].P.upload_values(u.data.data(), stream_);
             lv_[k].P.refresh_cast(stream_);
-            lv_[k].P.make_plan(u.indptr, st_->kernel_path, st_->staged_lanes, stream_);
-            HostCsr r = transpose(u);
+            range(k, d.sharded(k), b, e);
+            lv_[k].P.make_plan(u.indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e);
             lv_[k].R.upload_pattern(r, stream_);
             lv_[k].R.upload_values(r.data.data(), stream_);
             lv_[k].R.refresh_cast(stream_);
-            lv_[k].R.make_plan(r.indptr, st_->kernel_path, st_->staged_lanes, stream_);
-            r_host_.push_back(std::move(r));
-        }
-        GMG_CUDA(cudaStreamSynchronize(stream_));
-        hierarchy_ready_ = true;
-        pattern_ready_ = false;
-    }
-
-    // Symbolic phase, once per sparsity pattern of the lhs: patterns of A_k U_k and of every
-    // Galerkin operator, their tile plans, and the coarse workspace.
-    void setup_pattern(int64_t n, const int* indptr, const int* indices) {
-        const int64_t nnz = indptr[n];
-        a_indptr_h_.assign(indptr, indptr + n + 1);
-        a_indices_h_.assign(indices, indices + nnz);
-        HostCsr cur;
-        cur.rows = cur.cols = n;
-        cur.indptr = a_indptr_h_;
-        cur.indices = a_indices_h_;
-        lv_[0].A.upload_pattern(cur, stream_);
-        lv_[0].A.make_plan(cur.indptr, st_->kernel_path, st_->staged_lanes, stream_);
-        for (int k = 0; k < n_levels_; ++k) {
-            HostCsr ap = spgemm_symbolic(cur, st_->hier.U[k]);
-            HostCsr ac = spgemm_symbolic(r_host_[k], ap);
-            lv_[k].AP.upload_pattern(ap, stream_);
+            range(k + 1, d.sharded(k), b, e);  // rows of R are coarse points; sharded with the fine level
+            lv_[k].R.make_plan(r.indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e);
+            lv_[k].AP.upload_pattern(st_->ap_pat[k], stream_);
             lv_[k].AP.make_rowidx(stream_);
-            lv_[k + 1].A.upload_pattern(ac, stream_);
-            lv_[k + 1].A.make_rowidx(stream_);
-            lv_[k + 1].A.make_plan(ac.indptr, st_->kernel_path, st_->staged_lanes, stream_);
-            cur = std::move(ac);
         }
-        for (int k = 0; k <= n_levels_; ++k) lv_[k].dinv.ensure(std::max(lv_[k].n, 1));
+        for (int k = 0; k <= n_levels_; ++k) {
+            lv_[k].A.upload_pattern(st_->a_pat[k], stream_);
+            if (k > 0) lv_[k].A.make_rowidx(stream_);
+            range(k, d.sharded(k), b, e);
+            lv_[k].A.make_plan(st_->a_pat[k].indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e);
+            lv_[k].dinv.ensure(std::max(lv_[k].n, 1));
+        }
+        upload_halos();
         coarse_.setup(lv_[n_levels_].n, stream_);
         GMG_CUDA(cudaStreamSynchronize(stream_));
+        hierarchy_ready_ = true;
         pattern_ready_ = true;
         if (K_) allocate_vectors();
         invalidate_cycle();
+    }
+
+    // ---- multi-GPU: halo index lists on the device and the staging buffers of the exchanges
+    struct DevHalo {
+        std::vector<DeviceBuffer<int>> send_idx, recv_idx;  // per peer
+        std::vector<int> n_send, n_recv;
+    };
+
+    void upload_halos() {
+        const DistLayout& d = st_->dist;
+        for (auto& per_op : halo_) per_op.clear();
+        max_halo_ = 0;
+        if (d.world <= 1) return;
+        for (int hop = 0; hop < 3; ++hop) {
+            halo_[hop].resize(n_levels_ + 1);
+            for (int k = 0; k <= n_levels_; ++k) {
+                const HaloLists& h = d.halo[hop][k];
+                DevHalo& dh = halo_[hop][k];
+                if (h.send.empty()) continue;
+                dh.send_idx.resize(d.world), dh.recv_idx.resize(d.world);
+                dh.n_send.assign(d.world, 0), dh.n_recv.assign(d.world, 0);
+                size_t tot_s = 0, tot_r = 0;
+                for (int q = 0; q < d.world; ++q) {
+                    dh.n_send[q] = (int)h.send[q].size(), dh.n_recv[q] = (int)h.recv[q].size();
+                    if (dh.n_send[q]) dh.send_idx[q].upload(h.send[q], stream_);
+                    if (dh.n_recv[q]) dh.recv_idx[q].upload(h.recv[q], stream_);
+                    tot_s += h.send[q].size(), tot_r += h.recv[q].size();
+                }
+                max_halo_ = std::max(max_halo_, std::max(tot_s, tot_r));
+            }
+        }
+        GMG_CUDA(cudaStreamSynchronize(stream_));  // the host lists may be rebuilt
+    }
+
+    ncclDataType_t nccl_type() const { return sizeof(T) == 8 ? ncclDouble : ncclFloat; }
+
+    // Exchange the entries of the global-length vector v (K_ columns) that peers need / own.
+    void exchange_halo(const DevHalo& dh, T* v, cudaStream_t s) {
+        const int world = st_->dist.world;
+        size_t off = 0;
+        std::vector<size_t> soff(world), roff(world);
+        for (int q = 0; q < world; ++q) {
+            soff[q] = off;
+            if (dh.n_send[q]) launch_pack<T>(v, dh.send_idx[q].ptr, dh.n_send[q], K_, halo_send_.ptr + off * K_, s);
+            off += dh.n_send[q];
+        }
+        off = 0;
+        for (int q = 0; q < world; ++q) roff[q] = off, off += dh.n_recv[q];
+        GMG_NCCL(nccl().GroupStart());
+        for (int q = 0; q < world; ++q) {
+            if (dh.n_send[q]) GMG_NCCL(nccl().Send(halo_send_.ptr + soff[q] * K_, (size_t)dh.n_send[q] * K_, nccl_type(), q, comm_, s));
+            if (dh.n_recv[q]) GMG_NCCL(nccl().Recv(halo_recv_.ptr + roff[q] * K_, (size_t)dh.n_recv[q] * K_, nccl_type(), q, comm_, s));
+        }
+        GMG_NCCL(nccl().GroupEnd());
+        for (int q = 0; q < world; ++q)
+            if (dh.n_recv[q]) launch_unpack<T>(v, dh.recv_idx[q].ptr, dh.n_recv[q], K_, halo_recv_.ptr + roff[q] * K_, s);
+    }
+
+    // Every rank contributes its row range of a global-length vector (in place).
+    void allgather_rows(int level, T* v, cudaStream_t s) {
+        const DistLayout& d = st_->dist;
+        GMG_NCCL(nccl().GroupStart());
+        for (int q = 0; q < d.world; ++q) {
+            const size_t b = (size_t)d.ranges[level][q] * K_, cnt = (size_t)(d.ranges[level][q + 1] - d.ranges[level][q]) * K_;
+            if (cnt) GMG_NCCL(nccl().Broadcast(v + b, v + b, cnt, nccl_type(), q, comm_, s));
+        }
+        GMG_NCCL(nccl().GroupEnd());
+    }
+
+    void dist_init(const void* unique_id) override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        if (comm_) {
+            nccl().CommDestroy(comm_);
+            comm_ = nullptr;
+        }
+        if (st_->dist.world <= 1) return;
+        ncclUniqueId id;
+        std::memcpy(&id, unique_id, sizeof id);
+        GMG_NCCL(nccl().CommInitRank(&comm_, st_->dist.world, id, st_->dist.rank));
+        invalidate_hierarchy();
     }
 
     void allocate_vectors() {
@@ -569,6 +656,8 @@ private:
             lv_[k].x.ensure(count), lv_[k].t.ensure(count), lv_[k].b.ensure(count), lv_[k].r.ensure(count);
         }
         rhs64_.ensure((size_t)st_->n * K_);
+        if (max_halo_) halo_send_.ensure(max_halo_ * K_), halo_recv_.ensure(max_halo_ * K_);
+        norm_sums_.ensure(2 * kMaxRhsTile * kMaxNormChunks);
         if (sizeof(T) == 4) {
             x64_.ensure((size_t)st_->n * K_);
             const size_t nc = (size_t)lv_[n_levels_].n * K_;
@@ -602,9 +691,21 @@ private:
         return weights_.ptr + ((size_t)level * 2 + (post ? 1 : 0)) * kMaxSweeps + sweep;
     }
 
+    // Multi-GPU: before an operator gathers `v` through matrix `hop` of a sharded level, fetch the
+    // entries peers own (no-op on a single GPU and on replicated levels).
+    void push_halo(int level, int hop, T* v) {
+        const DistLayout& d = st_->dist;
+        if (!d.sharded(level)) return;
+        if (hop == HALO_P && !d.sharded(level + 1)) return;  // the coarse vector is replicated
+        Op op;
+        op.kind = OP_HALO, op.level = level, op.halo_op = hop, op.vec = v;
+        ops_.push_back(op);
+    }
+
     // Sweeps [first, last) of the pre- or post-smoothing sequence of level k.
     void push_sweeps(int k, bool post, int first, int last, T*& cur, T*& alt) {
         for (int i = first; i < last; ++i) {
+            push_halo(k, HALO_A, cur);
             Op op;
             op.kind = OP_JACOBI, op.level = k, op.epi = EPI_JACOBI, op.plan = &lv_[k].A.plan;
             op.args = base_args(lv_[k].A);
@@ -623,6 +724,7 @@ private:
         Level& f = lv_[k];
         Level& c = lv_[k + 1];
         push_sweeps(k, false, pre_done, p.pre_iters, cur, alt);
+        push_halo(k, HALO_A, cur);
         {   // res = b - A x
             Op op;
             op.kind = OP_RESIDUAL, op.level = k, op.epi = EPI_RESIDUAL, op.plan = &f.A.plan;
@@ -634,12 +736,19 @@ private:
         // is eps = omega D^-1 resRest, which the restriction writes as a by-product.
         const bool next_is_coarsest = (k + 1 == L);
         const int next_pre_done = (!next_is_coarsest && p.pre_iters >= 1) ? 1 : 0;
+        push_halo(k, HALO_R, f.r.ptr);
         {
             Op op;
             op.kind = OP_RESTRICT, op.level = k, op.epi = EPI_SPMV, op.plan = &f.R.plan;
             op.args = base_args(f.R);
             op.args.x = f.r.ptr, op.args.out = c.b.ptr;
             if (next_pre_done) op.args.out2 = c.x.ptr, op.args.dinv = c.dinv.ptr, op.args.omega_ptr = weight_ptr(k + 1, false, 0);
+            ops_.push_back(op);
+        }
+        if (st_->dist.sharded(k) && !st_->dist.sharded(k + 1)) {
+            // every rank restricted its own coarse rows; the next level is replicated
+            Op op;
+            op.kind = OP_ALLGATHER, op.level = k + 1, op.vec = c.b.ptr, op.vec2 = next_pre_done ? c.x.ptr : nullptr;
             ops_.push_back(op);
         }
         T* ccur = c.x.ptr;
@@ -658,6 +767,7 @@ private:
             push_vcycle(k + 1, ccur, calt, next_pre_done, false);
         }
         if (k + 1 == tail_level_) tail_end_ = ops_.size();
+        push_halo(k, HALO_P, ccur);
         {   // x = x + U eps. On level 0 an odd sweep count is evened out by writing to the other
             // buffer, so a cycle always ends in the buffer it started from (graph replay).
             Op op;
@@ -689,7 +799,7 @@ private:
         // levels small enough to live in L2 and be launch-latency bound run as one persistent
         // kernel (tail_kernel.cuh); never the finest level, whose streaming kernels are better
         tail_level_ = -1, tail_begin_ = tail_end_ = 0;
-        for (int k = 1; k <= n_levels_ && st_->tail_rows > 0; ++k)
+        for (int k = 1; k <= n_levels_ && st_->tail_rows > 0 && st_->dist.world <= 1; ++k)
             if (lv_[k].n <= st_->tail_rows) {
                 tail_level_ = k;
                 break;
@@ -713,6 +823,7 @@ private:
         }
         if (tail_level_ > 0 && tail_end_ > tail_begin_) collapse_tail();
         x_final_ = cur;
+        if (n_levels_ > 0) push_halo(0, HALO_A, cur);
         {   // residualCheck(LHS, b, x, stoppingCriteria) (multigrid_solver.cpp:1413)
             Op op;
             op.kind = OP_NORM, op.level = 0, op.epi = fused ? EPI_NORMJAC : EPI_NORM, op.plan = &lv_[0].A.plan;
@@ -819,6 +930,14 @@ private:
             case OP_ZERO:
                 GMG_CUDA(cudaMemsetAsync(op.zero_ptr, 0, op.zero_bytes, s));
                 break;
+            case OP_HALO:
+                exchange_halo(halo_[op.halo_op][op.level], op.vec, s);
+                launches += 2;
+                break;
+            case OP_ALLGATHER:
+                allgather_rows(op.level, op.vec, s);
+                if (op.vec2) allgather_rows(op.level, op.vec2, s);
+                break;
             case OP_TAIL: {
                 const int sms = tail_grid();
                 tail_kernel<T><<<sms, kTailThreads, 0, s>>>(reinterpret_cast<const TailOp<T>*>(tail_table_.ptr), n_tail_ops_, tail_bar_.ptr);
@@ -854,8 +973,16 @@ private:
                     ++chunks.n_chunks;
                     ++launches;
                 }
-                launch_norm_finalize(partials_.ptr, chunks, ctl_.ptr, hist_res_.ptr, hist_ms_.ptr, 1, cond, s);
-                ++launches;
+                if (st_->dist.world > 1) {
+                    // rows are split across ranks: sum the partial sums over the box first
+                    launch_norm_partial_sums(partials_.ptr, chunks, norm_sums_.ptr, s);
+                    GMG_NCCL(nccl().AllReduce(norm_sums_.ptr, norm_sums_.ptr, (size_t)2 * K_, ncclDouble, ncclSum, comm_, s));
+                    launch_norm_finalize_sums(norm_sums_.ptr, K_, ctl_.ptr, hist_res_.ptr, hist_ms_.ptr, s);
+                    launches += 2;
+                } else {
+                    launch_norm_finalize(partials_.ptr, chunks, ctl_.ptr, hist_res_.ptr, hist_ms_.ptr, 1, cond, s);
+                    ++launches;
+                }
                 break;
             }
             default: {
@@ -981,8 +1108,11 @@ private:
     DeviceBuffer<T> weights_;
     DeviceBuffer<int> q_indptr_, q_indices_;
     DeviceBuffer<double> q_vals_, q_b_, q_x_;
-    std::vector<int> a_indptr_h_, a_indices_h_;
-    std::vector<HostCsr> r_host_;
+    std::vector<DevHalo> halo_[3];
+    size_t max_halo_ = 0;
+    DeviceBuffer<T> halo_send_, halo_recv_;
+    DeviceBuffer<double> norm_sums_;
+    ncclComm_t comm_ = nullptr;
     bool hierarchy_ready_ = false, pattern_ready_ = false, staged_ = false, solved_ = false, cycle_dirty_ = true;
     bool numeric_ready_ = false;
     std::vector<Op> ops_, prologue_;

@@ -96,12 +96,13 @@ void spgemm_numeric(const HostCsr& a, const HostCsr& b, HostCsr& c) {
     }
 }
 
-std::vector<int> plan_row_tiles(const std::vector<int>& indptr, int max_rows, int max_nnz, int* max_tile_nnz) {
-    const int n = (int)indptr.size() - 1;
+std::vector<int> plan_row_tiles(const std::vector<int>& indptr, int max_rows, int max_nnz, int* max_tile_nnz,
+                                int row_begin, int row_end) {
+    const int n = row_end < 0 ? (int)indptr.size() - 1 : row_end;
     std::vector<int> tiles;
-    tiles.push_back(0);
+    tiles.push_back(row_begin);
     int worst = 0;
-    int r = 0;
+    int r = row_begin;
     while (r < n) {
         const int base = indptr[r] & ~3;  // slabs are fetched from a 16-byte aligned entry
         int e = r;

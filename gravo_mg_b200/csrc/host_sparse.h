@@ -36,7 +36,8 @@ void spgemm_numeric(const HostCsr& a, const HostCsr& b, HostCsr& c);
 // Row tiles for the staged kernels: consecutive row ranges with at most `max_rows` rows and
 // at most `max_nnz` stored entries each (a single row longer than max_nnz gets its own tile
 // and *max_tile_nnz reports it so the caller can fall back to the direct kernel).
+// Only rows [row_begin, row_end) are tiled (a rank's row range; the whole matrix by default).
 std::vector<int> plan_row_tiles(const std::vector<int>& indptr, int max_rows, int max_nnz,
-                                int* max_tile_nnz);
+                                int* max_tile_nnz, int row_begin = 0, int row_end = -1);
 
 }  // namespace gmg

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/gravomg_b200.h"
+#include "dist_plan.h"
 #include "hierarchy.h"
 #include "host_sparse.h"
 
@@ -26,6 +27,7 @@ public:
     virtual void level_op(int kind, int level, const double* a, const double* b, double* out, int sweeps) = 0;
     virtual void smoother_weights(int level, double* rho, double* pre, double* post) = 0;
     virtual void get_level_matrix(int level, int* indptr, int* indices, double* data) = 0;
+    virtual void dist_init(const void* nccl_unique_id) = 0;
     virtual void invalidate_hierarchy() = 0;
     virtual void invalidate_cycle() = 0;
     virtual bool level_info(int level, int64_t* rows, int64_t* nnz_a, int64_t* nnz_u) = 0;
@@ -47,6 +49,13 @@ struct SolverState {
                                      // default: measured slower than PDL-chained kernels ("Coarse tail")
     bool fuse_norm = true;           // stopping test fused with the next cycle's first sweep
     bool use_pdl = true;             // programmatic dependent launch of the row-product kernels
+    // ---- symbolic phase (host): patterns of every level operator for the staged lhs pattern
+    std::vector<HostCsr> r_host;     // R[k] = U[k]^T
+    std::vector<HostCsr> a_pat;      // pattern of A_k, k = 0..L (values unused)
+    std::vector<HostCsr> ap_pat;     // pattern of A_k U_k, k = 0..L-1
+    // ---- multi-GPU layout (world == 1: single GPU)
+    DistLayout dist;
+    int64_t replicate_rows = 300000; // levels with at most this many rows are replicated on every rank
     std::map<std::string, double> solver_timing;           // reference solverTiming keys
     std::vector<std::pair<double, double>> convergence;    // (elapsed ms, residue) per cycle
     int64_t last_launches = 0;
@@ -55,6 +64,13 @@ struct SolverState {
 };
 
 std::unique_ptr<EngineBase> make_engine(SolverState* state);
+
+// Host-only symbolic setup shared by the device engine and the layout queries of the C ABI.
+// transposes U (once per hierarchy) and computes the patterns of A_k U_k and of the Galerkin
+// operators for the given lhs pattern (multigrid_solver.cpp:1387-1392, structure only).
+void compute_level_patterns(SolverState& s, int64_t n, const int* indptr, const int* indices);
+// Row ranges of every level and the halo lists of every sharded operator for s.dist.rank / world.
+void compute_dist_layout(SolverState& s);
 
 }  // namespace gmg
 

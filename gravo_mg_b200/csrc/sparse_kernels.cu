@@ -75,6 +75,64 @@ __global__ void norm_finalize_kernel(const double* __restrict__ partials, NormCh
 
 // dinv_i = 1 / A_ii, and rho = max_i sum_j |A_ij| / A_ii (Gershgorin bound of the spectral radius
 // of D^-1 A, the upper end of the band the Chebyshev-weighted Jacobi sweeps damp).
+__global__ void norm_partial_sums_kernel(const double* __restrict__ partials, NormChunks chunks, double* __restrict__ sums) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int n_sums = 0;
+    for (int c = 0; c < chunks.n_chunks; ++c) {
+        const int nv = 2 * chunks.kt[c];
+        const double* part = partials + (size_t)c * kNormChunkStride;
+        for (int j = warp; j < nv; j += blockDim.x / 32) {
+            double s = 0.0;
+            for (int blk = lane; blk < chunks.n_blocks[c]; blk += 32) s += part[(size_t)blk * nv + j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) sums[n_sums + j] = s;
+        }
+        n_sums += nv;
+    }
+}
+
+__global__ void norm_finalize_sums_kernel(const double* __restrict__ sums, int K, CycleControl* ctl, double* hist_res,
+                                          double* hist_ms) {
+    if (threadIdx.x != 0 || ctl->done) return;
+    double residue = 0.0;
+    bool diverged = false;
+    if (ctl->criterion == 3) {
+        double tot = 0.0;
+        for (int k = 0; k < K; ++k) tot += sums[2 * k];
+        residue = sqrt(tot);
+        diverged = !(residue <= 1.7976931348623157e308);
+    } else {
+        for (int k = 0; k < K; ++k) {
+            const double rk = sqrt(sums[2 * k] / sums[2 * k + 1]);
+            if (k == 0 || rk > residue || rk != rk) residue = rk;
+            if (!(rk <= 1.7976931348623157e308) && sums[2 * k + 1] > 0.0) diverged = true;
+        }
+    }
+    ctl->residue = residue;
+    if (diverged) ctl->error |= 2;
+    const int it = ctl->iter;
+    hist_res[it] = residue;
+    hist_ms[it] = (double)(global_timer_ns() - ctl->t_start_ns) * 1e-6;
+    ctl->iter = it + 1;
+    ctl->done = !((residue > ctl->tol) && (it + 1 < ctl->max_iter));
+}
+
+template <typename T>
+__global__ void pack_kernel(const T* __restrict__ v, const int* __restrict__ idx, int n, int K, T* __restrict__ buf) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * K) return;
+    const int i = e / K, k = e - i * K;
+    buf[e] = v[(size_t)idx[i] * K + k];
+}
+template <typename T>
+__global__ void unpack_kernel(T* __restrict__ v, const int* __restrict__ idx, int n, int K, const T* __restrict__ buf) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * K) return;
+    const int i = e / K, k = e - i * K;
+    v[(size_t)idx[i] * K + k] = buf[e];
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) extract_dinv_kernel(int n, const int* __restrict__ rowptr,
                                                           const int* __restrict__ colidx,
@@ -278,8 +336,9 @@ int launch_one(SpmvArgs<T>& a, const SpmvPlan& plan, cudaStream_t stream) {
             default: grid = launch_staged<T, K, EPI, 8>(a, plan, stream); break;
         }
     } else {
+        if (plan.row_end >= 0) a.row_begin = plan.row_begin, a.n_rows = plan.row_end;
         const int rows_per_block = kDirectThreads / plan.lanes;
-        const int64_t want = ((int64_t)a.n_rows + rows_per_block - 1) / rows_per_block;
+        const int64_t want = ((int64_t)(a.n_rows - a.row_begin) + rows_per_block - 1) / rows_per_block;
         grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)num_sms() * 32);
         if (EPI == EPI_NORM || EPI == EPI_NORMJAC) grid = std::min(grid, kMaxNormBlocks);
         if (g_dry_run) return grid;
@@ -333,6 +392,32 @@ void launch_norm_finalize(const double* partials, const NormChunks& chunks, Cycl
     norm_finalize_kernel<<<1, 256, 0, stream>>>(partials, chunks, ctl, hist_res, hist_ms, record, cond_handle);
     GMG_CUDA(cudaGetLastError());
 }
+
+void launch_norm_partial_sums(const double* partials, const NormChunks& chunks, double* sums, cudaStream_t stream) {
+    norm_partial_sums_kernel<<<1, 256, 0, stream>>>(partials, chunks, sums);
+    GMG_CUDA(cudaGetLastError());
+}
+void launch_norm_finalize_sums(const double* sums, int K, CycleControl* ctl, double* hist_res, double* hist_ms,
+                               cudaStream_t stream) {
+    norm_finalize_sums_kernel<<<1, 32, 0, stream>>>(sums, K, ctl, hist_res, hist_ms);
+    GMG_CUDA(cudaGetLastError());
+}
+template <typename T>
+void launch_pack(const T* v, const int* idx, int n, int K, T* buf, cudaStream_t stream) {
+    if (n <= 0) return;
+    pack_kernel<T><<<(n * K + 255) / 256, 256, 0, stream>>>(v, idx, n, K, buf);
+    GMG_CUDA(cudaGetLastError());
+}
+template <typename T>
+void launch_unpack(T* v, const int* idx, int n, int K, const T* buf, cudaStream_t stream) {
+    if (n <= 0) return;
+    unpack_kernel<T><<<(n * K + 255) / 256, 256, 0, stream>>>(v, idx, n, K, buf);
+    GMG_CUDA(cudaGetLastError());
+}
+template void launch_pack<double>(const double*, const int*, int, int, double*, cudaStream_t);
+template void launch_pack<float>(const float*, const int*, int, int, float*, cudaStream_t);
+template void launch_unpack<double>(double*, const int*, int, int, const double*, cudaStream_t);
+template void launch_unpack<float>(float*, const int*, int, int, const float*, cudaStream_t);
 
 void launch_cycle_begin(CycleControl* ctl, int max_iter, int criterion, double tol, int n_cols, cudaStream_t stream) {
     cycle_begin_kernel<<<1, 1, 0, stream>>>(ctl, max_iter, criterion, tol, n_cols);

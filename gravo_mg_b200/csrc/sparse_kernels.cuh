@@ -45,7 +45,8 @@ struct CycleControl {
 
 template <typename T>
 struct SpmvArgs {
-    int n_rows = 0;
+    int n_rows = 0;                    // direct path: rows [row_begin, n_rows) are processed
+    int row_begin = 0;
     int ld = 1;                        // leading dimension of every vector (= total K of the solve)
     const int* rowptr = nullptr;
     const int* colidx = nullptr;
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(kDirectThreads) spmv_direct_kernel(const SpmvA
     for (int j = 0; j < 2 * K; ++j) nrm[j] = 0.0;
 
     // block-uniform trip count so the shuffles below always see full warps
-    for (int first = blockIdx.x * rows_per_block; first < a.n_rows; first += gridDim.x * rows_per_block) {
+    for (int first = a.row_begin + blockIdx.x * rows_per_block; first < a.n_rows; first += gridDim.x * rows_per_block) {
         const int row = first + threadIdx.x / LANES;
         const bool active = row < a.n_rows;
         T acc[K];

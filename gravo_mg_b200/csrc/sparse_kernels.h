@@ -9,6 +9,7 @@ struct SpmvPlan {
     int path = 1;            // 0 staged (TMA), 1 direct
     int lanes = 8;           // direct: threads per row (1, 2, 4, 8, 16, 32)
     int staged_lanes = 1;    // staged: threads per row (1, 2, 4, 8); 1 sums in CSR order
+    int row_begin = 0, row_end = -1;  // rows this plan covers (a rank's range; -1 = all)
     int n_tiles = 0;         // staged
     int stage_elems = 0;     // staged: entries per stage (multiple of 4)
     int stage_rows = 0;      // staged: rows per tile = kStagedThreads / staged_lanes
@@ -45,6 +46,15 @@ void set_launch_pdl(bool on);
 // `cond_handle` != 0 additionally drives a CUDA graph while-node (cudaGraphSetConditional).
 void launch_norm_finalize(const double* partials, const NormChunks& chunks, CycleControl* ctl, double* hist_res,
                           double* hist_ms, int record, unsigned long long cond_handle, cudaStream_t stream);
+// Multi-GPU stopping test: local NORM partials -> sums[2K] (then all-reduced) -> loop state.
+void launch_norm_partial_sums(const double* partials, const NormChunks& chunks, double* sums, cudaStream_t stream);
+void launch_norm_finalize_sums(const double* sums, int K, CycleControl* ctl, double* hist_res, double* hist_ms,
+                               cudaStream_t stream);
+// Halo exchange staging: buf[i, :] = v[idx[i], :] and back (K columns, row-major).
+template <typename T>
+void launch_pack(const T* v, const int* idx, int n, int K, T* buf, cudaStream_t stream);
+template <typename T>
+void launch_unpack(T* v, const int* idx, int n, int K, const T* buf, cudaStream_t stream);
 void launch_cycle_begin(CycleControl* ctl, int max_iter, int criterion, double tol, int n_cols, cudaStream_t stream);
 
 constexpr int kMaxSweeps = 16;        // pre / post sweeps per level the weight table holds

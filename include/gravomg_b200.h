@@ -124,6 +124,28 @@ int gmg_fetch_solution(gmg_handle h, double* x_out);
 int gmg_residual(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t* a_indices, const double* a_data,
                  const double* rhs, const double* x, int32_t K, int32_t type, double* out);
 
+/* ---- multi-GPU: row-range domain decomposition over the GPUs of one box (new design: the
+ * reference is single-process). One process per GPU, SPMD: every rank creates the
+ * same solver, configures (rank, world), joins the NCCL communicator and then makes the SAME
+ * gmg_solve / gmg_stage_system / gmg_solve_staged / gmg_fetch_solution calls with the same global
+ * inputs; every rank gets the full solution back. Levels with more than `replicate_rows` rows are
+ * sharded by contiguous row ranges with NCCL halo exchanges before each operator; smaller
+ * levels, the Galerkin setup and the coarse direct solve are replicated (-1 keeps the default). */
+int gmg_dist_configure(gmg_handle h, int32_t rank, int32_t world, int64_t replicate_rows);
+/* ncclGetUniqueId on the calling rank (usually 0); the caller broadcasts the bytes to all ranks. */
+int gmg_dist_unique_id(void* id_out, int64_t capacity, int64_t* size);
+/* ncclCommInitRank on the handle's device (collective over all ranks). */
+int gmg_dist_init(gmg_handle h, const void* id, int64_t size);
+/* Host-only: row ranges and halo lists for the given lhs pattern (what staging computes), so the
+ * layout can be inspected and tested without a device. */
+int gmg_dist_layout(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t* a_indices);
+/* ranges[world + 1] of a level; *replicated = 1 when every rank computes all rows of it. */
+int gmg_dist_ranges(gmg_handle h, int32_t level, int64_t* ranges, int32_t* replicated);
+/* Halo lists of operator op (0: A_k, 1: R_k = U_k^T, 2: U_k) on a level towards one peer: global
+ * indices this rank sends / receives, ascending. Query sizes with send == recv == NULL. */
+int gmg_dist_halo(gmg_handle h, int32_t op, int32_t level, int32_t peer, int32_t* send, int64_t* n_send, int32_t* recv,
+                  int64_t* n_recv);
+
 /* ---- timing maps and convergence trace (multigrid_solver.h:157-159; core.cpp:118-128) ----
  * which: 0 = hierarchyTiming, 1 = solverTiming. Keys come back comma separated, in the
  * alphabetical order std::map gives the reference's CSV writer (utility.cpp:106-131). */

@@ -1,0 +1,59 @@
+"""Worker of tests/test_distributed_gpu.py: one rank per GPU (launched with torch.distributed.run).
+Solves the same system sharded over all ranks and on this rank's GPU alone, and compares."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    import gravomg
+    from gravo_mg_b200 import synth
+
+    out = {}
+    for name, (n_side, replicate_rows, kind) in {"two_sharded_levels": (300, 5000, "poisson"), "one_sharded_level": (300, 50000, "poisson"),
+                                                 "smoothing_K3": (200, 3000, "smoothing")}.items():
+        V, F = synth.torus_grid(n_side, n_side)
+        V, S, M, neigh = synth.mesh_operators(V, F)
+        lhs, rhs = synth.poisson_system(S, M) if kind == "poisson" else synth.smoothing_system(V, S, M)
+        kw = dict(lower_bound=500, tolerance=1e-6, device=local)
+        single = gravomg.MultigridSolver(V, neigh, M, **kw)
+        single.solver.set_option("lanes", 1)
+        x1 = single.solve(lhs, rhs)
+        sharded = gravomg.MultigridSolver(V, neigh, M, **kw)
+        sharded.solver.set_option("lanes", 1)
+        sharded.distribute(replicate_rows=replicate_rows)
+        xs = sharded.solve(lhs, rhs)
+        levels = [sharded.solver.dist_ranges(k) for k in range(len(single.prolongation_matrices) + 1)]
+        m = M.diagonal()
+        res = float(np.sqrt(((lhs @ xs - rhs) ** 2 * m[:, None]).sum(0) / ((rhs ** 2) * m[:, None]).sum(0)).max())
+        out[name] = {
+            "iters_single": single.solver_timing["iterations"], "iters_sharded": sharded.solver_timing["iterations"],
+            "bitwise_equal": bool(np.array_equal(x1, xs)), "max_abs_diff": float(np.abs(x1 - xs).max()),
+            "residual": res, "residue_reported": sharded.solver_timing["residue"],
+            "sharded_levels": [int(not rep) for _, rep in levels], "rows": [int(r[-1]) for r, _ in levels],
+        }
+        # all ranks hold the same full solution
+        t = torch.from_numpy(xs.copy()).cuda()
+        ref = t.clone()
+        dist.broadcast(ref, src=0)
+        out[name]["same_on_all_ranks"] = bool(torch.equal(t, ref))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, out)
+    if rank == 0:
+        print("DIST_RESULT " + json.dumps(gathered))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

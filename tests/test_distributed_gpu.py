@@ -1,0 +1,40 @@
+"""Sharded V-cycle on >= 2 GPUs against the single-GPU solve (run with `gpurun --gpus 2`)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_count():
+    try:
+        import torch
+
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs at least two GPUs")
+def test_sharded_solve_equals_single_gpu_solve():
+    n = min(_gpu_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("DIST_RESULT ")][-1]
+    per_rank = json.loads(line[len("DIST_RESULT "):])
+    assert len(per_rank) == n
+    for result in per_rank:
+        for name, r in result.items():
+            assert sum(r["sharded_levels"]) >= 1, (name, r)
+            assert r["iters_single"] == r["iters_sharded"], (name, r)
+            # per-row arithmetic does not depend on the partition: identical iterates (P4)
+            assert r["bitwise_equal"], (name, r)
+            assert r["residual"] <= 1e-6 and r["same_on_all_ranks"], (name, r)
+    assert sum(per_rank[0]["two_sharded_levels"]["sharded_levels"]) == 2
