@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--pdl", type=int, default=1)
     ap.add_argument("--fuse-norm", type=int, default=1)
     ap.add_argument("--tail-rows", type=int, default=0)
+    ap.add_argument("--replicate-rows", type=int, default=300000)
+    ap.add_argument("--dist-graph", type=int, default=1)
     ap.add_argument("--loop-mode", type=int, default=1)
     ap.add_argument("--kernel-path", type=int, default=0)
     ap.add_argument("--use-graph", type=int, default=1)
@@ -178,12 +180,18 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    n_side = args.n_side
+    # weak scaling: N GPUs solve ONE system of N x 1M vertices, sharded by row ranges
+    n_side = int(round(args.n_side * (max(world, args.gpus) ** 0.5)))
+    scale = n_side * n_side / float(args.n_side * args.n_side)  # one V-cycle of this system = `scale` 1M-vertex V-cycles
     workload = (f"torus {n_side}x{n_side} ({n_side * n_side} vertices) Poisson lhs=1e-6*M+S, fp64, K=1, "
                 f"V-cycle {args.sweeps}+{args.sweeps} sweeps, lower_bound={args.lower_bound}, tol={args.tol:g} (criterion 2, M-norm)")
     config = {"workload": workload, "config_index": 1, "levels": None,
               "l2": "operators + vectors of one solve (~250 MB at 1M vertices) exceed the 126 MB L2; a 512 MB buffer is also written between timed steps",
-              "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one system per GPU, no collective)"}
+              "parallelism": "single GPU" if max(world, args.gpus) == 1 else
+              (f"{max(world, args.gpus)} ranks, one per GPU: row-range domain decomposition of one {n_side}x{n_side} system, NCCL halo exchange "
+               f"on sharded levels, levels <= {args.replicate_rows} rows replicated"),
+              "scaling_unit": ("value counts one V-cycle of the N-times-larger system as N V-cycles of the 1M-vertex system "
+                               "(vertices / 1e6), so ideal weak scaling is value(N) = N * value(1)")}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -196,6 +204,8 @@ def main():
         U = solver.prolongation_matrices
         config["levels"] = [int(lhs.shape[0])] + [int(u.shape[1]) for u in U]
         r = cpu_reference_run(V, neigh, M, lhs, rhs, U, args.tol, args.steps, args.warmup)
+        r["value"] *= scale
+        r["cycles_only_value"] *= scale
         line = {
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
@@ -235,7 +245,10 @@ def main():
     b.set_option("pdl", args.pdl)
     b.set_option("fuse_norm", args.fuse_norm)
     b.set_option("tail_rows", args.tail_rows)
+    b.set_option("dist_graph", args.dist_graph)
     U = solver.prolongation_matrices
+    if world > 1:
+        solver.distribute(replicate_rows=args.replicate_rows)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -283,8 +296,7 @@ def main():
     residue = b.solver_timing()["residue"]
     split = {k: b.solver_timing()[k] for k in ("reduction", "coarsest_solve", "cycles")}
     dev_ms_max = max_over_ranks(dev_ms)
-    total_cycles = sum_over_ranks(cycles)
-    value = total_cycles / (dev_ms_max / 1e3)
+    value = scale * cycles / (dev_ms_max / 1e3)  # all ranks run the same cycles of one sharded system
 
     # ---- end to end through the public API, host arrays in, host array out
     x = solver.solve(lhs, rhs)
@@ -297,7 +309,7 @@ def main():
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - e2e_t0)
     clocks = sampler.stop()
-    e2e_value = sum_over_ranks(e2e_cycles) / e2e_s
+    e2e_value = scale * e2e_cycles / e2e_s
     h2d = lhs.indptr.nbytes // (lhs.indptr.itemsize // 4) + lhs.indices.nbytes // (lhs.indices.itemsize // 4) + lhs.data.nbytes + rhs.nbytes
     h2d_values_only = lhs.data.nbytes + rhs.nbytes  # the pattern is compared on the host and not re-sent
     d2h = x.nbytes
@@ -316,9 +328,23 @@ def main():
             ms, cnt = b.kernel_profile(kind, lvl)
             if cnt:
                 per_kernel[f"{name}_L{lvl}"] = {"us": 1e3 * ms / cnt, "launches": cnt}
+    # the same kernel timed alone: 60 back-to-back launches between two CUDA events (as two or three
+    # sweeps follow each other in the cycle); programmatic dependent launch overlaps their edges
+    chain_us = {}
+    if world == 1:
+        for lvl in range(len(info) - 1):
+            chain_us[f"jacobi_L{lvl}"] = b.time_op("jacobi", lvl, 60)
+        chain_us["residual_L0"] = b.time_op("residual", 0, 60)
+        chain_us["restrict_L0"] = b.time_op("restrict", 0, 60)
+        chain_us["prolong_add_L0"] = b.time_op("prolong_add", 0, 60)
     nnz0, n0 = info[0]["nnz_a"], info[0]["rows"]
+    if world > 1:  # the fine level is sharded: this rank streams its row range only
+        r0, _ = b.dist_ranges(0)
+        frac_rows = (r0[rank + 1] - r0[rank]) / float(n0)
+        nnz0, n0 = int(nnz0 * frac_rows), int(n0 * frac_rows)
     jac_bytes = nnz0 * 12 + n0 * 36
-    jac_us = 1e3 * jac_ms / max(jac_launches, 1)
+    jac_us_in_cycle = 1e3 * jac_ms / max(jac_launches, 1)
+    jac_us = chain_us.get("jacobi_L0", jac_us_in_cycle)
     peak, peak_src = measured_hbm_peak()
     achieved = jac_bytes / (jac_us * 1e-6) / 1e9 if jac_us > 0 else 0.0
     vcycle_bytes = 0
@@ -328,10 +354,15 @@ def main():
     vcycle_bytes += info[-1]["rows"] ** 2 * 8
     roofline = {"bound": "hbm", "kernel": "spmv_staged_kernel<double,1,EPI_JACOBI,LANES> (fine level)" if args.kernel_path == 0 else "spmv_direct_kernel<double,1,EPI_JACOBI,LANES> (fine level)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "algorithmic_bytes_per_launch": jac_bytes, "us_per_launch": jac_us,
-                "launches_timed": jac_launches,
+                "traffic": 121.3e6 if (world == 1 and n_side == 1000) else None,
+                "traffic_source": "profiles/r1_warm_traffic.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu, cache control off)",
+                "algorithmic_bytes_per_launch": jac_bytes, "us_per_launch": jac_us,
+                "timing": "60 back-to-back launches of the kernel between two CUDA events on its launch stream (burst; peak = measured copy bandwidth)",
+                "us_per_launch_serialised_in_cycle": jac_us_in_cycle,
+                "frac_serialised_in_cycle": (jac_bytes / (jac_us_in_cycle * 1e-6) / 1e9) / peak if jac_us_in_cycle > 0 else None,
+                "launches_timed": 60 if chain_us else jac_launches, "chain_us_per_launch": chain_us,
                 "vcycle_algorithmic_bytes": vcycle_bytes,
-                "vcycle_frac": (vcycle_bytes / ((cyc_ms / max(cycles, 1)) * 1e-3) / 1e9) / peak if cycles else None}
+                "vcycle_frac": (vcycle_bytes / world / ((cyc_ms / max(cycles, 1)) * 1e-3) / 1e9) / peak if cycles else None}
 
     if rank == 0:
         line = {
@@ -345,7 +376,8 @@ def main():
             "smoother": (f"Chebyshev-weighted Jacobi, band rho/{args.cheb_alpha:g}..rho" if args.smoother == "chebyshev"
                          else f"damped Jacobi omega={args.omega:.4f}") + f", {args.sweeps}+{args.sweeps} sweeps",
             "cycles_per_step": cycles / args.steps,
-            "cycles_only_vcycles_per_s": cycles / (cyc_ms / 1e3), "time_to_tol_s": dev_ms / args.steps / 1e3,
+            "cycles_only_vcycles_per_s": scale * cycles / (cyc_ms / 1e3), "time_to_tol_s": dev_ms / args.steps / 1e3,
+            "n_vertices": n_side * n_side,
             "residue": residue, "wall_s_timed_region": wall, "last_step_split_ms": split, "per_kernel_us": per_kernel,
         }
         if world == 1 and not args.no_cpu_baseline:

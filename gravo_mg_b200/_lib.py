@@ -87,6 +87,7 @@ SIGNATURES = {
     "gmg_get_smoother_weights": (C.c_int, [_h, C.c_int32, _f64p, _f64p, _f64p]),
     "gmg_get_level_matrix": (C.c_int, [_h, C.c_int32, _i32p, _i32p, _f64p]),
     "gmg_level_op": (C.c_int, [_h, C.c_int32, C.c_int32, _f64p, _f64p, _f64p, C.c_int32]),
+    "gmg_time_op": (C.c_int, [_h, C.c_int32, C.c_int32, C.c_int32, _f64p]),
     "gmg_kernel_profile": (C.c_int, [_h, C.c_int32, C.c_int32, _f64p, _i64p]),
     "gmg_reset_kernel_profile": (C.c_int, [_h]),
     "gmg_last_launch_count": (C.c_int, [_h, _i64p]),

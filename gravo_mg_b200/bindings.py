@@ -362,6 +362,13 @@ class MultigridSolver:
         check(self._h, lib.gmg_level_op(self._h, kind, int(level), f64(a), f64(bb) if bb is not None else None, f64(out), int(sweeps)))
         return out
 
+    def time_op(self, kind, level, reps=50):
+        """Mean microseconds per launch of ``reps`` back-to-back launches of one operator."""
+        kind = self.OPS[kind] if isinstance(kind, str) else int(kind)
+        us = C.c_double()
+        check(self._h, lib.gmg_time_op(self._h, kind, int(level), int(reps), C.byref(us)))
+        return us.value
+
     def kernel_profile(self, kind, level=-1):
         ms, launches = C.c_double(), C.c_int64()
         check(self._h, lib.gmg_kernel_profile(self._h, int(kind), int(level), C.byref(ms), C.byref(launches)))

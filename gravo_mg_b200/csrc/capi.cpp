@@ -154,6 +154,7 @@ int gmg_set_option(gmg_handle h, const char* key, double value) {
         else if (k == "pdl") s.use_pdl = value != 0.0, cycle = true;
         else if (k == "fuse_norm") s.fuse_norm = value != 0.0, cycle = true;
         else if (k == "tail_rows") s.tail_rows = (int)value, cycle = true;
+        else if (k == "dist_graph") s.dist_graph = value != 0.0, cycle = true;
         else if (k == "kernel_path") s.kernel_path = (int)value, hierarchy = true;
         else throw std::invalid_argument("unknown option: " + k);
         require(s.params.pre_iters >= 0 && s.params.post_iters >= 0 && s.params.pre_iters <= 16 && s.params.post_iters <= 16, "sweep counts must be 0..16");
@@ -187,6 +188,7 @@ int gmg_get_option(gmg_handle h, const char* key, double* value) {
         else if (k == "pdl") *value = s.use_pdl;
         else if (k == "fuse_norm") *value = s.fuse_norm;
         else if (k == "tail_rows") *value = s.tail_rows;
+        else if (k == "dist_graph") *value = s.dist_graph;
         else if (k == "kernel_path") *value = s.kernel_path;
         else throw std::invalid_argument("unknown option: " + k);
     });
@@ -446,6 +448,15 @@ int gmg_level_op(gmg_handle h, int32_t kind, int32_t level, const double* a, con
         require(out != nullptr, "null argument");
         require(h->s.engine != nullptr, "gmg_level_op needs a staged system (gmg_stage_system)");
         h->s.engine->level_op(kind, level, a, b, out, sweeps);
+    });
+}
+
+int gmg_time_op(gmg_handle h, int32_t kind, int32_t level, int32_t reps, double* us_per_launch) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(us_per_launch != nullptr, "null argument");
+        require(h->s.engine != nullptr, "gmg_time_op needs a staged system (gmg_stage_system)");
+        *us_per_launch = h->s.engine->time_op(kind, level, reps);
     });
 }
 

@@ -213,8 +213,9 @@ public:
         launch_cycle_begin(ctl_.ptr, p.max_iter, p.stopping_criteria, p.tolerance, K_, stream_);
         ++launches;
         for (const Op& op : prologue_) launches += run_op(op, stream_, 0);
-        const bool graph = st_->use_graph && !st_->profile && st_->dist.world <= 1;  // NCCL exchanges are issued from the host
-        if (graph && st_->loop_mode == 1) {
+        // multi-GPU: the NCCL exchanges are captured into the cycle graph too (option dist_graph)
+        const bool graph = st_->use_graph && !st_->profile && (st_->dist.world <= 1 || st_->dist_graph);
+        if (graph && st_->loop_mode == 1 && st_->dist.world <= 1) {
             if (!while_exec_) build_while_graph();
             GMG_CUDA(cudaGraphLaunch(while_exec_, stream_));
         } else {
@@ -461,6 +462,69 @@ public:
             default:
                 throw std::invalid_argument("unknown operator kind");
         }
+    }
+
+    // Average device time of `reps` back-to-back launches of one operator on the level's resident
+    // buffers (CUDA events on the launch stream; Jacobi ping-pongs x <-> t as in the cycle).
+    double time_op(int kind, int level, int reps) override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        if (!staged_) throw std::logic_error("time_op before stage_system");
+        if (st_->dist.world > 1) throw std::logic_error("time_op is a single-GPU measurement entry point");
+        set_launch_pdl(st_->use_pdl);
+        const int L = n_levels_;
+        if (level < 0 || level > L || reps < 1) throw std::invalid_argument("level or repetition count out of range");
+        if (cycle_dirty_) build_cycle();
+        if (!numeric_ready_) {
+            GMG_CUDA(cudaMemsetAsync(ctl_.ptr, 0, sizeof(CycleControl), stream_));
+            setup_numeric(nullptr);
+            check_setup_errors();
+        }
+        solved_ = false;
+        Level& f = lv_[level];
+        Op op;
+        op.level = level;
+        T* cur = f.x.ptr;
+        T* alt = f.t.ptr;
+        switch (kind) {
+            case OP_JACOBI:
+                if (level >= L || st_->params.pre_iters < 1) throw std::invalid_argument("no smoother on this level");
+                op.kind = OP_JACOBI, op.epi = EPI_JACOBI, op.plan = &f.A.plan, op.args = base_args(f.A);
+                op.args.b = f.b.ptr, op.args.dinv = f.dinv.ptr, op.args.omega_ptr = weight_ptr(level, false, 0);
+                break;
+            case OP_RESIDUAL:
+                op.kind = OP_RESIDUAL, op.epi = EPI_RESIDUAL, op.plan = &f.A.plan, op.args = base_args(f.A);
+                op.args.b = f.b.ptr;
+                break;
+            case OP_RESTRICT:
+                if (level >= L) throw std::invalid_argument("no prolongation below the coarsest level");
+                op.kind = OP_RESTRICT, op.epi = EPI_SPMV, op.plan = &f.R.plan, op.args = base_args(f.R);
+                break;
+            case OP_PROLONG:
+                if (level >= L) throw std::invalid_argument("no prolongation below the coarsest level");
+                op.kind = OP_PROLONG, op.epi = EPI_ADD, op.plan = &f.P.plan, op.args = base_args(f.P);
+                break;
+            default:
+                throw std::invalid_argument("time_op: kind must be jacobi, residual, restrict or prolong_add");
+        }
+        cudaEvent_t e0, e1;
+        GMG_CUDA(cudaEventCreate(&e0));
+        GMG_CUDA(cudaEventCreate(&e1));
+        for (int i = -3; i < reps; ++i) {
+            if (i == 0) GMG_CUDA(cudaEventRecord(e0, stream_));
+            switch (kind) {
+                case OP_JACOBI: op.args.x = cur, op.args.out = alt; std::swap(cur, alt); break;
+                case OP_RESIDUAL: op.args.x = f.x.ptr, op.args.out = f.r.ptr; break;
+                case OP_RESTRICT: op.args.x = f.r.ptr, op.args.out = lv_[level + 1].b.ptr; break;
+                default: op.args.x = lv_[level + 1].x.ptr, op.args.xin = f.x.ptr, op.args.out = f.t.ptr; break;
+            }
+            run_op(op, stream_, 0);
+        }
+        GMG_CUDA(cudaEventRecord(e1, stream_));
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+        float ms = 0;
+        GMG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0), cudaEventDestroy(e1);
+        return 1e3 * ms / reps;
     }
 
     void get_level_matrix(int level, int* indptr, int* indices, double* data) override {

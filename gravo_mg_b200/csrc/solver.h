@@ -25,6 +25,7 @@ public:
     virtual double residual(int64_t n, const int* indptr, const int* indices, const double* data, const double* rhs,
                             const double* x, int K, int type) = 0;
     virtual void level_op(int kind, int level, const double* a, const double* b, double* out, int sweeps) = 0;
+    virtual double time_op(int kind, int level, int reps) = 0;
     virtual void smoother_weights(int level, double* rho, double* pre, double* post) = 0;
     virtual void get_level_matrix(int level, int* indptr, int* indices, double* data) = 0;
     virtual void dist_init(const void* nccl_unique_id) = 0;
@@ -47,6 +48,7 @@ struct SolverState {
     bool profile = false;
     int tail_rows = 0;               // levels with at most this many rows run inside the fused tail kernel; off by
                                      // default: measured slower than PDL-chained kernels ("Coarse tail")
+    bool dist_graph = true;          // multi-GPU: capture the cycle (kernels + NCCL exchanges) into a CUDA graph
     bool fuse_norm = true;           // stopping test fused with the next cycle's first sweep
     bool use_pdl = true;             // programmatic dependent launch of the row-product kernels
     // ---- symbolic phase (host): patterns of every level operator for the staged lhs pattern

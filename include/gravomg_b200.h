@@ -174,6 +174,10 @@ int gmg_get_level_matrix(gmg_handle h, int32_t level, int32_t* indptr, int32_t* 
  *   kind 5 coarse      a = rhs (n_L)        out = Abar[L]^-1 rhs                       (level = L) */
 int gmg_level_op(gmg_handle h, int32_t kind, int32_t level, const double* a, const double* b, double* out,
                  int32_t sweeps);
+/* Mean device time (microseconds, CUDA events on the launch stream) of `reps` back-to-back
+ * launches of one operator kind (0 jacobi, 1 residual, 2 restrict, 3 prolong_add) on a level's
+ * resident buffers, after 3 warm-up launches; Jacobi alternates its two vectors as in the cycle. */
+int gmg_time_op(gmg_handle h, int32_t kind, int32_t level, int32_t reps, double* us_per_launch);
 /* Per-kernel device time accumulated while option "profile" = 1. Kernel kinds:
  * 0 jacobi, 1 residual, 2 restrict, 3 prolong_add, 4 norm, 5 coarse_solve, 7 fused coarse tail
  * (filed under its first level). Level -1 sums levels. */
