@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--loop-mode", type=int, default=1)
     ap.add_argument("--kernel-path", type=int, default=0)
     ap.add_argument("--use-graph", type=int, default=1)
+    ap.add_argument("--xfer-threads", type=int, default=-1, help="host threads staging caller buffers (-1 auto, 0 plain pageable copies)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -246,6 +247,7 @@ def main():
     b.set_option("fuse_norm", args.fuse_norm)
     b.set_option("tail_rows", args.tail_rows)
     b.set_option("dist_graph", args.dist_graph)
+    b.set_option("xfer_threads", args.xfer_threads)
     U = solver.prolongation_matrices
     if world > 1:
         solver.distribute(replicate_rows=args.replicate_rows)
@@ -303,9 +305,15 @@ def main():
     barrier()
     e2e_t0 = time.perf_counter()
     e2e_cycles = 0
+    e2e_split = {"stage_host_ms": 0.0, "device_solve_ms": 0.0, "fetch_host_ms": 0.0}
     for _ in range(args.steps):
         x = solver.solve(lhs, rhs)
         e2e_cycles += int(solver.solver_timing["iterations"])
+        tt = b.transfer_timing()
+        e2e_split["stage_host_ms"] += tt["stage_host_ms"] / args.steps
+        e2e_split["fetch_host_ms"] += tt["fetch_host_ms"] / args.steps
+        e2e_split["device_solve_ms"] += solver.solver_timing["solver_total"] / args.steps
+    e2e_split["transfer_threads"] = tt["transfer_threads"]
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - e2e_t0)
     clocks = sampler.stop()
@@ -370,8 +378,9 @@ def main():
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_values_only), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "note": f"host CSR pattern ({h2d - h2d_values_only} B) is compared against the staged one on the host and not re-sent"},
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "split": e2e_split,
+                    "note": (f"caller-owned pageable numpy arrays; values + rhs go through pinned chunks filled by host threads; the CSR pattern "
+                             f"({h2d - h2d_values_only} B) is compared against the staged one on the host and not re-sent")},
             "gpu_launches": int(launches), "roofline": roofline,
             "smoother": (f"Chebyshev-weighted Jacobi, band rho/{args.cheb_alpha:g}..rho" if args.smoother == "chebyshev"
                          else f"damped Jacobi omega={args.omega:.4f}") + f", {args.sweeps}+{args.sweeps} sweeps",

@@ -224,6 +224,10 @@ class MultigridSolver:
     def solver_timing(self):
         return self._timing(1)
 
+    def transfer_timing(self):
+        """Host side of the last stage / fetch: milliseconds, bytes, whether the staged pattern was reused."""
+        return self._timing(2)
+
     def convergence(self):
         count = C.c_int32(0)
         check(self._h, lib.gmg_get_convergence(self._h, None, None, C.byref(count)))

@@ -156,10 +156,12 @@ int gmg_set_option(gmg_handle h, const char* key, double value) {
         else if (k == "tail_rows") s.tail_rows = (int)value, cycle = true;
         else if (k == "dist_graph") s.dist_graph = value != 0.0, cycle = true;
         else if (k == "kernel_path") s.kernel_path = (int)value, hierarchy = true;
+        else if (k == "xfer_threads") s.xfer_threads = (int)value;
         else throw std::invalid_argument("unknown option: " + k);
         require(s.params.pre_iters >= 0 && s.params.post_iters >= 0 && s.params.pre_iters <= 16 && s.params.post_iters <= 16, "sweep counts must be 0..16");
         require(s.params.smoother == GMG_SMOOTHER_JACOBI || s.params.smoother == GMG_SMOOTHER_CHEBYSHEV, "unknown smoother");
         require(s.params.cheb_alpha > 1.0, "cheb_alpha must be > 1");
+        require(s.xfer_threads >= -1 && s.xfer_threads <= 64, "xfer_threads must be -1 (auto), 0 (off) or 1..64");
         require(s.staged_lanes == 0 || s.staged_lanes == 1 || s.staged_lanes == 2 || s.staged_lanes == 4 || s.staged_lanes == 8, "lanes must be 0, 1, 2, 4 or 8");
         if (s.engine && hierarchy) s.engine->invalidate_hierarchy();
         if (s.engine && cycle) s.engine->invalidate_cycle();
@@ -190,6 +192,7 @@ int gmg_get_option(gmg_handle h, const char* key, double* value) {
         else if (k == "tail_rows") *value = s.tail_rows;
         else if (k == "dist_graph") *value = s.dist_graph;
         else if (k == "kernel_path") *value = s.kernel_path;
+        else if (k == "xfer_threads") *value = s.xfer_threads;
         else throw std::invalid_argument("unknown option: " + k);
     });
 }
@@ -279,7 +282,7 @@ int gmg_stage_system(gmg_handle h, int64_t n, const int32_t* a_indptr, const int
     if (!h) return 1;
     return guarded(h, [&] {
         require(a_indptr && a_indices && a_data && rhs, "null argument");
-        engine(h).stage_system(n, a_indptr, a_indices, a_data, rhs, K);
+        engine(h).stage_system(n, a_indptr, a_indices, a_data, rhs, K, true);
     });
 }
 
@@ -302,7 +305,7 @@ int gmg_solve(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t* a
     return guarded(h, [&] {
         require(a_indptr && a_indices && a_data && rhs && x_out, "null argument");
         gmg::EngineBase& e = engine(h);
-        e.stage_system(n, a_indptr, a_indices, a_data, rhs, K);
+        e.stage_system(n, a_indptr, a_indices, a_data, rhs, K, false);
         e.solve_staged();
         e.fetch_solution(x_out);
     });
@@ -398,7 +401,7 @@ int gmg_timing_keys(gmg_handle h, int32_t which, char* buf, int64_t buflen) {
     if (!h) return 1;
     return guarded(h, [&] {
         require(buf && buflen > 0, "null argument");
-        const auto& m = which == 0 ? h->s.hier.timing : h->s.solver_timing;
+        const auto& m = which == 0 ? h->s.hier.timing : which == 2 ? h->s.transfer_timing : h->s.solver_timing;
         std::string joined;
         for (const auto& kv : m) {
             if (!joined.empty()) joined += ',';
@@ -413,7 +416,7 @@ int gmg_get_timing(gmg_handle h, int32_t which, const char* key, double* out) {
     if (!h) return 1;
     return guarded(h, [&] {
         require(key && out, "null argument");
-        const auto& m = which == 0 ? h->s.hier.timing : h->s.solver_timing;
+        const auto& m = which == 0 ? h->s.hier.timing : which == 2 ? h->s.transfer_timing : h->s.solver_timing;
         auto it = m.find(key);
         require(it != m.end(), "unknown timing key");
         *out = it->second;

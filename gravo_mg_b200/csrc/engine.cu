@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "dense_coarse.h"
+#include "host_xfer.h"
 #include "nccl_dl.h"
 #include "solver.h"
 #include "sparse_kernels.h"
@@ -129,6 +130,7 @@ public:
 
     ~Engine() override {
         cudaSetDevice(st_->params.device);
+        xfer_.reset();
         drop_graphs();
         if (comm_) nccl().CommDestroy(comm_);
         for (auto& e : ev_) cudaEventDestroy(e);
@@ -149,39 +151,83 @@ public:
 
     // ------------------------------------------------------------------ staging
     void stage_system(int64_t n, const int* indptr, const int* indices, const double* data, const double* rhs,
-                      int K) override {
+                      int K, bool wait) override {
         GMG_CUDA(cudaSetDevice(st_->params.device));
         if (n != st_->n) throw std::invalid_argument("lhs has a different number of rows than the point set of the constructor");
         if (K < 1 || K > kMaxRhsTile * kMaxNormChunks) throw std::invalid_argument("number of right-hand sides must be 1..32");
         if (indptr[0] != 0) throw std::invalid_argument("lhs indptr must start at 0");
         const int64_t nnz = indptr[n];
+        const auto t0 = std::chrono::steady_clock::now();
         if (!hierarchy_ready_) pattern_ready_ = false;
-        const bool same = pattern_ready_ && !st_->a_pat.empty() && st_->a_pat[0].rows == n &&
-                          (int64_t)st_->a_pat[0].indices.size() == nnz &&
-                          std::memcmp(st_->a_pat[0].indptr.data(), indptr, (n + 1) * sizeof(int)) == 0 &&
-                          std::memcmp(st_->a_pat[0].indices.data(), indices, nnz * sizeof(int)) == 0;
-        if (!same) setup_pattern(n, indptr, indices);
-        lv_[0].A.upload_values(data, stream_);
-        numeric_ready_ = false;
         if (K != K_) {
             K_ = K;
-            allocate_vectors();
+            if (pattern_ready_) allocate_vectors();
             invalidate_cycle();
         }
-        GMG_CUDA(cudaMemcpyAsync(rhs64_.ptr, rhs, (size_t)n * K * sizeof(double), cudaMemcpyHostToDevice, stream_));
-        GMG_CUDA(cudaStreamSynchronize(stream_));
+        const bool same_shape = pattern_ready_ && !st_->a_pat.empty() && st_->a_pat[0].rows == n &&
+                                (int64_t)st_->a_pat[0].indices.size() == nnz;
+        HostTransfer* xf = transfer();
+        bool same = false;
+        if (same_shape && xf) {
+            // the usual repeated solve: same pattern, new values. Values and rhs stream to HBM through
+            // pinned chunks while the same worker threads compare the pattern with the staged one.
+            std::vector<HostTransfer::Copy> copies = value_copies(data, rhs, nnz, n, K);
+            std::vector<HostTransfer::Compare> compares(2);
+            compares[0].a = st_->a_pat[0].indptr.data(), compares[0].b = indptr, compares[0].bytes = (size_t)(n + 1) * sizeof(int);
+            compares[1].a = st_->a_pat[0].indices.data(), compares[1].b = indices, compares[1].bytes = (size_t)nnz * sizeof(int);
+            same = xf->upload_and_compare(copies, compares, stream_);
+        } else if (same_shape) {
+            same = std::memcmp(st_->a_pat[0].indptr.data(), indptr, (n + 1) * sizeof(int)) == 0 &&
+                   std::memcmp(st_->a_pat[0].indices.data(), indices, nnz * sizeof(int)) == 0;
+        }
+        const bool uploaded = same && xf;
+        if (!same) {
+            GMG_CUDA(cudaStreamSynchronize(stream_));  // a speculative upload may still be in flight
+            setup_pattern(n, indptr, indices);
+        }
+        if (!uploaded) {
+            if (xf) {
+                xf->upload_and_compare(value_copies(data, rhs, nnz, n, K), {}, stream_);
+            } else {
+                lv_[0].A.upload_values(data, stream_);
+                GMG_CUDA(cudaMemcpyAsync(rhs64_.ptr, rhs, (size_t)n * K * sizeof(double), cudaMemcpyHostToDevice, stream_));
+            }
+        }
+        numeric_ready_ = false;
+        if (wait || !xf) GMG_CUDA(cudaStreamSynchronize(stream_));
         staged_ = true;
+        auto& tt = st_->transfer_timing;
+        tt["stage_host_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        tt["pattern_reused"] = same ? 1.0 : 0.0;
+        tt["h2d_bytes"] = (double)((size_t)nnz * sizeof(double) + (size_t)n * K * sizeof(double) +
+                                   (same ? 0 : (size_t)(n + 1 + nnz) * sizeof(int)));
+        tt["transfer_threads"] = xf ? (double)xf->threads() : 0.0;
+    }
+
+    std::vector<HostTransfer::Copy> value_copies(const double* data, const double* rhs, int64_t nnz, int64_t n, int K) {
+        std::vector<HostTransfer::Copy> c(2);
+        c[0].dev = lv_[0].A.v64.ptr, c[0].host = data, c[0].bytes = (size_t)nnz * sizeof(double);
+        c[1].dev = rhs64_.ptr, c[1].host = rhs, c[1].bytes = (size_t)n * K * sizeof(double);
+        return c;
     }
 
     void fetch_solution(double* x_out) override {
         GMG_CUDA(cudaSetDevice(st_->params.device));
         if (!solved_) throw std::logic_error("fetch_solution before solve_staged");
+        const auto t0 = std::chrono::steady_clock::now();
         const size_t count = (size_t)st_->n * K_;
         if (st_->dist.sharded(0)) allgather_rows(0, x_final_, stream_);
         if (sizeof(T) == 4) launch_cast_f32_f64(reinterpret_cast<const float*>(x_final_), x64_.ptr, count, stream_);
         const double* src = sizeof(T) == 4 ? x64_.ptr : reinterpret_cast<const double*>(x_final_);
-        GMG_CUDA(cudaMemcpyAsync(x_out, src, count * sizeof(double), cudaMemcpyDeviceToHost, stream_));
-        GMG_CUDA(cudaStreamSynchronize(stream_));
+        if (HostTransfer* xf = transfer()) {
+            GMG_CUDA(cudaStreamSynchronize(stream_));
+            xf->download(x_out, src, count * sizeof(double));
+        } else {
+            GMG_CUDA(cudaMemcpyAsync(x_out, src, count * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+            GMG_CUDA(cudaStreamSynchronize(stream_));
+        }
+        st_->transfer_timing["fetch_host_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        st_->transfer_timing["d2h_bytes"] = (double)(count * sizeof(double));
     }
 
     // ------------------------------------------------------------------ solve
@@ -714,6 +760,22 @@ private:
         invalidate_hierarchy();
     }
 
+    // Worker threads + pinned slots for caller-owned buffers (host_xfer.h); nullptr when the
+    // option xfer_threads is 0 (plain cudaMemcpyAsync from pageable memory).
+    HostTransfer* transfer() {
+        int want = st_->xfer_threads;
+        if (want < 0) want = std::min(8, std::max(1, (int)std::thread::hardware_concurrency() / 2));
+        if (want == 0) {
+            xfer_.reset();
+            return nullptr;
+        }
+        if (!xfer_ || xfer_->threads() != want) {
+            xfer_.reset();
+            xfer_.reset(new HostTransfer(st_->params.device, want));
+        }
+        return xfer_.get();
+    }
+
     void allocate_vectors() {
         for (int k = 0; k <= n_levels_; ++k) {
             const size_t count = (size_t)std::max(lv_[k].n, 1) * K_;
@@ -1159,6 +1221,7 @@ private:
     };
 
     SolverState* st_;
+    std::unique_ptr<HostTransfer> xfer_;
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev_[4] = {};
     std::vector<Level> lv_;

@@ -18,8 +18,9 @@ namespace gmg {
 class EngineBase {
 public:
     virtual ~EngineBase() = default;
+    // wait = false: return once the copies are enqueued (the caller's buffers have been read)
     virtual void stage_system(int64_t n, const int* indptr, const int* indices, const double* data, const double* rhs,
-                              int K) = 0;
+                              int K, bool wait) = 0;
     virtual void solve_staged() = 0;
     virtual void fetch_solution(double* x_out) = 0;
     virtual double residual(int64_t n, const int* indptr, const int* indices, const double* data, const double* rhs,
@@ -51,6 +52,8 @@ struct SolverState {
     bool dist_graph = true;          // multi-GPU: capture the cycle (kernels + NCCL exchanges) into a CUDA graph
     bool fuse_norm = true;           // stopping test fused with the next cycle's first sweep
     bool use_pdl = true;             // programmatic dependent launch of the row-product kernels
+    int xfer_threads = -1;           // host threads staging caller buffers through pinned chunks (host_xfer.h);
+                                     // -1 = min(8, cores / 2), 0 = plain pageable cudaMemcpyAsync
     // ---- symbolic phase (host): patterns of every level operator for the staged lhs pattern
     std::vector<HostCsr> r_host;     // R[k] = U[k]^T
     std::vector<HostCsr> a_pat;      // pattern of A_k, k = 0..L (values unused)
@@ -59,6 +62,7 @@ struct SolverState {
     DistLayout dist;
     int64_t replicate_rows = 300000; // levels with at most this many rows are replicated on every rank
     std::map<std::string, double> solver_timing;           // reference solverTiming keys
+    std::map<std::string, double> transfer_timing;         // host side of the last stage / fetch (not a reference map)
     std::vector<std::pair<double, double>> convergence;    // (elapsed ms, residue) per cycle
     int64_t last_launches = 0;
     std::string error;

@@ -85,7 +85,8 @@ const char* gmg_last_error(gmg_handle h);
  * "pdl" (0/1 programmatic dependent launch of consecutive kernels), "fuse_norm" (0/1 stopping
  * test and next cycle's first sweep in one kernel), "tail_rows" (levels with at most this many
  * rows run inside one persistent kernel with grid barriers; 0 = one kernel per operator), "profile" (0/1 per-kernel
- * event timing). */
+ * event timing), "xfer_threads" (host threads that stage caller-owned buffers through pinned chunks during
+ * gmg_solve / gmg_stage_system / gmg_fetch_solution; -1 = auto, 0 = plain pageable copies). */
 int gmg_set_option(gmg_handle h, const char* key, double value);
 int gmg_get_option(gmg_handle h, const char* key, double* value);
 
@@ -147,7 +148,8 @@ int gmg_dist_halo(gmg_handle h, int32_t op, int32_t level, int32_t peer, int32_t
                   int64_t* n_recv);
 
 /* ---- timing maps and convergence trace (multigrid_solver.h:157-159; core.cpp:118-128) ----
- * which: 0 = hierarchyTiming, 1 = solverTiming. Keys come back comma separated, in the
+ * which: 0 = hierarchyTiming, 1 = solverTiming, 2 = host side of the last transfer (stage_host_ms,
+ * fetch_host_ms, h2d_bytes, d2h_bytes, pattern_reused, transfer_threads; not a reference map). Keys come back comma separated, in the
  * alphabetical order std::map gives the reference's CSV writer (utility.cpp:106-131). */
 int gmg_timing_keys(gmg_handle h, int32_t which, char* buf, int64_t buflen);
 int gmg_get_timing(gmg_handle h, int32_t which, const char* key, double* out);

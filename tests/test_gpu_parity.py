@@ -429,6 +429,42 @@ def test_injected_hierarchy_and_repeated_solves(ico10k):
     np.testing.assert_array_equal(x1_again, xb)
 
 
+def test_host_transfer_paths_and_pattern_change(torus_mid):
+    """gmg_solve with caller-owned host arrays: the pinned-chunk worker threads (host_xfer.h) and
+    the plain pageable copies move the same bytes; a changed sparsity pattern of the same shape
+    is detected by the threaded comparison and re-staged."""
+    p = torus_mid
+    rng = np.random.default_rng(3)
+    rhs3 = rng.standard_normal((p.lhs.shape[0], 3))
+    ref = None
+    for threads in (0, 1, 3, 8):
+        solver = p.new_solver(tolerance=1e-6)
+        solver.solver.set_option("xfer_threads", threads)
+        x1 = solver.solve(p.lhs, p.rhs)
+        x1b = solver.solve(p.lhs, p.rhs)                 # second call: speculative upload + pattern compare
+        tt = solver.solver.transfer_timing()
+        assert tt["pattern_reused"] == 1.0 and tt["transfer_threads"] == threads
+        assert tt["h2d_bytes"] == p.lhs.data.nbytes + p.rhs.nbytes and tt["d2h_bytes"] == x1.nbytes
+        x3 = solver.solve(p.lhs, rhs3)                   # K 1 -> 3 on the staged pattern
+        # same shape and nnz, different pattern: swap two column indices inside one row and keep the
+        # matrix the same operator by swapping the values too -> different arrays, same solution
+        lhs2 = p.lhs.copy()
+        r = 17
+        a, b = lhs2.indptr[r], lhs2.indptr[r] + 1
+        lhs2.indices[[a, b]] = lhs2.indices[[b, a]]
+        lhs2.data[[a, b]] = lhs2.data[[b, a]]
+        lhs2.has_sorted_indices = False
+        x2 = solver.solve(lhs2, p.rhs)
+        assert solver.solver.transfer_timing()["pattern_reused"] == 0.0
+        np.testing.assert_array_equal(x1, x1b)
+        # same operator, one row summed in another order: equal up to rounding of that row
+        assert np.abs(x2 - x1).max() <= 1e-9 * np.abs(x1).max()
+        if ref is None:
+            ref = (x1, x3)
+        np.testing.assert_array_equal(x1, ref[0])
+        np.testing.assert_array_equal(x3, ref[1])
+
+
 def test_timing_maps_and_csv_writers(ico_small, tmp_path):
     p = ico_small
     s = p.new_solver(tolerance=1e-6)
