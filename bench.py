@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--tail-rows", type=int, default=0)
     ap.add_argument("--replicate-rows", type=int, default=300000)
     ap.add_argument("--dist-graph", type=int, default=1)
+    ap.add_argument("--p2p", type=int, default=1, help="multi-GPU: 1 halo pushes over NVLink peer memory, 0 NCCL send/recv")
     ap.add_argument("--loop-mode", type=int, default=1)
     ap.add_argument("--kernel-path", type=int, default=0)
     ap.add_argument("--use-graph", type=int, default=1)
@@ -189,8 +190,10 @@ def main():
     config = {"workload": workload, "config_index": 1, "levels": None,
               "l2": "operators + vectors of one solve (~250 MB at 1M vertices) exceed the 126 MB L2; a 512 MB buffer is also written between timed steps",
               "parallelism": "single GPU" if max(world, args.gpus) == 1 else
-              (f"{max(world, args.gpus)} ranks, one per GPU: row-range domain decomposition of one {n_side}x{n_side} system, NCCL halo exchange "
-               f"on sharded levels, levels <= {args.replicate_rows} rows replicated"),
+              (f"{max(world, args.gpus)} ranks, one per GPU: row-range domain decomposition of one {n_side}x{n_side} system, "
+               + ("halo rows pushed into peer HBM over NVLink (CUDA IPC arena, flag handshake), whole solve one while-graph per rank"
+                  if args.p2p else "NCCL send/recv halo exchange") +
+               f" on sharded levels, levels <= {args.replicate_rows} rows replicated"),
               "scaling_unit": ("value counts one V-cycle of the N-times-larger system as N V-cycles of the 1M-vertex system "
                                "(vertices / 1e6), so ideal weak scaling is value(N) = N * value(1)")}
 
@@ -248,6 +251,7 @@ def main():
     b.set_option("tail_rows", args.tail_rows)
     b.set_option("dist_graph", args.dist_graph)
     b.set_option("xfer_threads", args.xfer_threads)
+    b.set_option("p2p", args.p2p)
     U = solver.prolongation_matrices
     if world > 1:
         solver.distribute(replicate_rows=args.replicate_rows)

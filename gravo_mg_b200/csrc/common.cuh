@@ -30,27 +30,34 @@ template <typename T>
 struct DeviceBuffer {
     T* ptr = nullptr;
     size_t count = 0;
+    bool owned = true;   // false: a view into memory owned elsewhere (the multi-GPU peer arena)
     DeviceBuffer() = default;
     DeviceBuffer(const DeviceBuffer&) = delete;
     DeviceBuffer& operator=(const DeviceBuffer&) = delete;
-    DeviceBuffer(DeviceBuffer&& o) noexcept : ptr(o.ptr), count(o.count) { o.ptr = nullptr, o.count = 0; }
+    DeviceBuffer(DeviceBuffer&& o) noexcept : ptr(o.ptr), count(o.count), owned(o.owned) { o.ptr = nullptr, o.count = 0, o.owned = true; }
     DeviceBuffer& operator=(DeviceBuffer&& o) noexcept {
         if (this != &o) {
             release();
-            ptr = o.ptr, count = o.count;
-            o.ptr = nullptr, o.count = 0;
+            ptr = o.ptr, count = o.count, owned = o.owned;
+            o.ptr = nullptr, o.count = 0, o.owned = true;
         }
         return *this;
     }
     ~DeviceBuffer() { release(); }
     void release() {
-        if (ptr) cudaFree(ptr);
+        if (ptr && owned) cudaFree(ptr);
         ptr = nullptr;
         count = 0;
+        owned = true;
+    }
+    // Point at `n` elements owned by someone else.
+    void view(T* p, size_t n) {
+        release();
+        ptr = p, count = n, owned = false;
     }
     // Grow-only allocation; contents are not preserved.
     void ensure(size_t n, size_t pad = 0) {
-        if (n + pad <= count && ptr) return;
+        if (n + pad <= count && ptr && owned) return;
         release();
         GMG_CUDA(cudaMalloc((void**)&ptr, (n + pad ? n + pad : 1) * sizeof(T)));
         count = n + pad;

@@ -11,6 +11,7 @@
 #include "dense_coarse.h"
 #include "host_xfer.h"
 #include "nccl_dl.h"
+#include "peer_exchange.h"
 #include "solver.h"
 #include "sparse_kernels.h"
 #include "tail_kernel.cuh"
@@ -132,6 +133,10 @@ public:
         cudaSetDevice(st_->params.device);
         xfer_.reset();
         drop_graphs();
+        try {
+            release_peer_arena(false);
+        } catch (...) {
+        }
         if (comm_) nccl().CommDestroy(comm_);
         for (auto& e : ev_) cudaEventDestroy(e);
         for (auto& e : prof_events_) cudaEventDestroy(e);
@@ -261,7 +266,7 @@ public:
         for (const Op& op : prologue_) launches += run_op(op, stream_, 0);
         // multi-GPU: the NCCL exchanges are captured into the cycle graph too (option dist_graph)
         const bool graph = st_->use_graph && !st_->profile && (st_->dist.world <= 1 || st_->dist_graph);
-        if (graph && st_->loop_mode == 1 && st_->dist.world <= 1) {
+        if (graph && st_->loop_mode == 1 && (st_->dist.world <= 1 || use_p2p())) {
             if (!while_exec_) build_while_graph();
             GMG_CUDA(cudaGraphLaunch(while_exec_, stream_));
         } else {
@@ -306,6 +311,7 @@ public:
         solved_ = true;
         if (ctl_host_->error & 1) throw std::runtime_error("an operator has a missing, non-positive or non-finite diagonal entry (Jacobi smoother needs A_ii > 0)");
         if (ctl_host_->error & 4) throw std::runtime_error("coarsest-level Cholesky broke down: the Galerkin operator is not positive definite");
+        if (ctl_host_->error & 8) throw std::runtime_error("multi-GPU halo exchange timed out waiting for a peer rank (ranks out of step, or a peer failed)");
         if (ctl_host_->error & 2) throw std::runtime_error("residual became non-finite (diverged); try a smaller omega");
     }
 
@@ -643,6 +649,7 @@ private:
             b = sharded ? (int)d.begin(level) : 0;
             e = sharded ? (int)d.end(level) : -1;
         };
+        release_peer_arena();
         lv_.clear();
         lv_.resize(n_levels_ + 1);
         lv_[0].n = (int)st_->n;
@@ -776,19 +783,95 @@ private:
         return xfer_.get();
     }
 
+    bool use_p2p() const { return st_->dist.world > 1 && st_->p2p; }
+
     void allocate_vectors() {
-        for (int k = 0; k <= n_levels_; ++k) {
-            const size_t count = (size_t)std::max(lv_[k].n, 1) * K_;
-            lv_[k].x.ensure(count), lv_[k].t.ensure(count), lv_[k].b.ensure(count), lv_[k].r.ensure(count);
+        release_peer_arena();
+        if (use_p2p()) {
+            build_peer_arena();
+        } else {
+            for (int k = 0; k <= n_levels_; ++k) {
+                const size_t count = (size_t)std::max(lv_[k].n, 1) * K_;
+                lv_[k].x.ensure(count), lv_[k].t.ensure(count), lv_[k].b.ensure(count), lv_[k].r.ensure(count);
+            }
         }
         rhs64_.ensure((size_t)st_->n * K_);
-        if (max_halo_) halo_send_.ensure(max_halo_ * K_), halo_recv_.ensure(max_halo_ * K_);
+        if (max_halo_ && !use_p2p()) halo_send_.ensure(max_halo_ * K_), halo_recv_.ensure(max_halo_ * K_);
         norm_sums_.ensure(2 * kMaxRhsTile * kMaxNormChunks);
         if (sizeof(T) == 4) {
             x64_.ensure((size_t)st_->n * K_);
             const size_t nc = (size_t)lv_[n_levels_].n * K_;
             coarse_b64_.ensure(nc), coarse_x64_.ensure(nc);
         }
+    }
+
+    // ---- multi-GPU peer arena (peer_exchange.h): mailbox + the vectors of every level in one
+    // allocation with the same layout on every rank, exported / imported with CUDA IPC.
+    void build_peer_arena() {
+        const DistLayout& d = st_->dist;
+        if (d.world > kMaxPeers) throw std::invalid_argument("peer-memory halo exchange supports at most 8 ranks (one NVSwitch box)");
+        if (!comm_) throw std::logic_error("multi-GPU layout configured but gmg_dist_init has not been called");
+        auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        size_t bytes = align(sizeof(PeerMailbox));
+        std::vector<size_t> off;
+        for (int k = 0; k <= n_levels_; ++k) {
+            const size_t vb = align((size_t)std::max(lv_[k].n, 1) * K_ * sizeof(T));
+            for (int j = 0; j < 4; ++j) off.push_back(bytes), bytes += vb;
+        }
+        GMG_CUDA(cudaMalloc(&arena_, bytes));
+        arena_bytes_ = bytes;
+        GMG_CUDA(cudaMemsetAsync(arena_, 0, bytes, stream_));
+        peer_local_.ensure(4);
+        GMG_CUDA(cudaMemsetAsync(peer_local_.ptr, 0, 4 * sizeof(unsigned long long), stream_));
+        for (int k = 0; k <= n_levels_; ++k) {
+            const size_t count = (size_t)std::max(lv_[k].n, 1) * K_;
+            char* base = static_cast<char*>(arena_);
+            lv_[k].x.view(reinterpret_cast<T*>(base + off[4 * k + 0]), count);
+            lv_[k].t.view(reinterpret_cast<T*>(base + off[4 * k + 1]), count);
+            lv_[k].b.view(reinterpret_cast<T*>(base + off[4 * k + 2]), count);
+            lv_[k].r.view(reinterpret_cast<T*>(base + off[4 * k + 3]), count);
+        }
+        // every rank's mailbox must be zero before any peer can reach it
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+        cudaIpcMemHandle_t mine;
+        GMG_CUDA(cudaIpcGetMemHandle(&mine, arena_));
+        std::vector<cudaIpcMemHandle_t> all(d.world);
+        ipc_buf_.ensure((size_t)d.world * sizeof(cudaIpcMemHandle_t));
+        GMG_CUDA(cudaMemcpyAsync(ipc_buf_.ptr + (size_t)d.rank * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice, stream_));
+        GMG_NCCL(nccl().AllGather(ipc_buf_.ptr + (size_t)d.rank * sizeof mine, ipc_buf_.ptr, sizeof mine, ncclChar, comm_, stream_));
+        GMG_CUDA(cudaMemcpyAsync(all.data(), ipc_buf_.ptr, all.size() * sizeof mine, cudaMemcpyDeviceToHost, stream_));
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+        fabric_ = PeerFabric();
+        fabric_.rank = d.rank, fabric_.world = d.world;
+        fabric_.box = static_cast<PeerMailbox*>(arena_);
+        fabric_.epoch = peer_local_.ptr;
+        fabric_.ticket = reinterpret_cast<unsigned int*>(peer_local_.ptr + 1);
+        for (int q = 0; q < d.world; ++q) {
+            if (q == d.rank) continue;
+            GMG_CUDA(cudaIpcOpenMemHandle(&peer_base_[q], all[q], cudaIpcMemLazyEnablePeerAccess));
+            fabric_.peer_delta[q] = static_cast<char*>(peer_base_[q]) - static_cast<char*>(arena_);
+        }
+        box_barrier();  // nobody pushes before everybody has mapped everybody
+    }
+
+    void box_barrier() {
+        GMG_NCCL(nccl().AllReduce(norm_sums_.ptr, norm_sums_.ptr, 1, ncclDouble, ncclSum, comm_, stream_));
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+    }
+
+    void release_peer_arena(bool collective = true) {
+        if (!arena_) return;
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+        for (auto& pb : peer_base_) {
+            if (pb) cudaIpcCloseMemHandle(pb);
+            pb = nullptr;
+        }
+        // peers unmap before the owner frees (every rank re-allocates at the same point of the program)
+        if (collective && comm_) box_barrier();
+        for (auto& l : lv_) l.x.release(), l.t.release(), l.b.release(), l.r.release();
+        cudaFree(arena_);
+        arena_ = nullptr, arena_bytes_ = 0;
+        drop_graphs();
     }
 
     void set_initial_guess() {
@@ -1057,12 +1140,32 @@ private:
                 GMG_CUDA(cudaMemsetAsync(op.zero_ptr, 0, op.zero_bytes, s));
                 break;
             case OP_HALO:
-                exchange_halo(halo_[op.halo_op][op.level], op.vec, s);
-                launches += 2;
+                if (use_p2p()) {
+                    const DevHalo& dh = halo_[op.halo_op][op.level];
+                    PeerPushArgs<T> a;
+                    a.v = op.vec, a.K = K_;
+                    for (int q = 0; q < st_->dist.world; ++q)
+                        if (!dh.n_send.empty() && dh.n_send[q]) a.idx[q] = dh.send_idx[q].ptr, a.count[q] = dh.n_send[q];
+                    launch_peer_push<T>(a, fabric_, ctl_.ptr, s);
+                    launches += 1;
+                } else {
+                    exchange_halo(halo_[op.halo_op][op.level], op.vec, s);
+                    launches += 2;
+                }
                 break;
             case OP_ALLGATHER:
-                allgather_rows(op.level, op.vec, s);
-                if (op.vec2) allgather_rows(op.level, op.vec2, s);
+                if (use_p2p()) {
+                    const DistLayout& d = st_->dist;
+                    PeerPushArgs<T> a;
+                    a.v = op.vec, a.v2 = op.vec2, a.K = K_;
+                    for (int q = 0; q < d.world; ++q)
+                        if (q != d.rank) a.first[q] = (int)d.begin(op.level), a.count[q] = (int)(d.end(op.level) - d.begin(op.level));
+                    launch_peer_push<T>(a, fabric_, ctl_.ptr, s);
+                    launches += 1;
+                } else {
+                    allgather_rows(op.level, op.vec, s);
+                    if (op.vec2) allgather_rows(op.level, op.vec2, s);
+                }
                 break;
             case OP_TAIL: {
                 const int sms = tail_grid();
@@ -1099,7 +1202,11 @@ private:
                     ++chunks.n_chunks;
                     ++launches;
                 }
-                if (st_->dist.world > 1) {
+                if (use_p2p()) {
+                    // rows are split across ranks: partial sums travel through the peers' mailboxes
+                    launch_peer_norm(partials_.ptr, chunks, K_, fabric_, ctl_.ptr, hist_res_.ptr, hist_ms_.ptr, cond, s);
+                    ++launches;
+                } else if (st_->dist.world > 1) {
                     // rows are split across ranks: sum the partial sums over the box first
                     launch_norm_partial_sums(partials_.ptr, chunks, norm_sums_.ptr, s);
                     GMG_NCCL(nccl().AllReduce(norm_sums_.ptr, norm_sums_.ptr, (size_t)2 * K_, ncclDouble, ncclSum, comm_, s));
@@ -1240,6 +1347,12 @@ private:
     DeviceBuffer<T> halo_send_, halo_recv_;
     DeviceBuffer<double> norm_sums_;
     ncclComm_t comm_ = nullptr;
+    void* arena_ = nullptr;            // peer arena (multi-GPU, option p2p)
+    size_t arena_bytes_ = 0;
+    void* peer_base_[kMaxPeers] = {};  // peers' arenas mapped into this process
+    PeerFabric fabric_;
+    DeviceBuffer<unsigned long long> peer_local_;
+    DeviceBuffer<unsigned char> ipc_buf_;
     bool hierarchy_ready_ = false, pattern_ready_ = false, staged_ = false, solved_ = false, cycle_dirty_ = true;
     bool numeric_ready_ = false;
     std::vector<Op> ops_, prologue_;

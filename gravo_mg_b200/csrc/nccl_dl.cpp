@@ -37,6 +37,7 @@ const NcclApi& nccl() {
             bind(lib, "ncclSend", api.Send);
             bind(lib, "ncclRecv", api.Recv);
             bind(lib, "ncclAllReduce", api.AllReduce);
+            bind(lib, "ncclAllGather", api.AllGather);
             bind(lib, "ncclBroadcast", api.Broadcast);
             bind(lib, "ncclGetErrorString", api.GetErrorString);
         } catch (const std::exception& e) {

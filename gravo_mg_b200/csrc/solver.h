@@ -50,6 +50,8 @@ struct SolverState {
     int tail_rows = 0;               // levels with at most this many rows run inside the fused tail kernel; off by
                                      // default: measured slower than PDL-chained kernels ("Coarse tail")
     bool dist_graph = true;          // multi-GPU: capture the cycle (kernels + NCCL exchanges) into a CUDA graph
+    bool p2p = true;                 // multi-GPU: halos and norms through NVLink peer memory (peer_exchange.h);
+                                     // false: pack / ncclSend / ncclRecv / unpack and ncclAllReduce
     bool fuse_norm = true;           // stopping test fused with the next cycle's first sweep
     bool use_pdl = true;             // programmatic dependent launch of the row-product kernels
     int xfer_threads = -1;           // host threads staging caller buffers through pinned chunks (host_xfer.h);

@@ -41,36 +41,7 @@ __global__ void norm_finalize_kernel(const double* __restrict__ partials, NormCh
         n_sums += nv;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const int K = n_sums / 2;
-        double residue = 0.0;
-        bool diverged = false;
-        if (ctl->criterion == 3) {
-            double tot = 0.0;
-            for (int k = 0; k < K; ++k) tot += sums[2 * k];
-            residue = sqrt(tot);
-            diverged = !(residue <= 1.7976931348623157e308);
-        } else {
-            for (int k = 0; k < K; ++k) {  // maxCoeff over the right-hand sides
-                const double rk = sqrt(sums[2 * k] / sums[2 * k + 1]);
-                if (k == 0 || rk > residue || rk != rk) residue = rk;
-                // 0/0 (an all-zero right-hand side) is NaN upstream too and simply ends the loop;
-                // a non-finite residual of a non-zero system means the smoother diverged
-                if (!(rk <= 1.7976931348623157e308) && sums[2 * k + 1] > 0.0) diverged = true;
-            }
-        }
-        ctl->residue = residue;
-        if (diverged) ctl->error |= 2;
-        if (record) {
-            const int it = ctl->iter;
-            hist_res[it] = residue;
-            hist_ms[it] = (double)(global_timer_ns() - ctl->t_start_ns) * 1e-6;
-            ctl->iter = it + 1;
-            const int keep_going = (residue > ctl->tol) && (it + 1 < ctl->max_iter);
-            ctl->done = !keep_going;
-            if (cond_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, keep_going ? 1u : 0u);
-        }
-    }
+    if (threadIdx.x == 0) apply_stopping_rule(sums, n_sums / 2, ctl, hist_res, hist_ms, record, cond_handle);
 }
 
 // dinv_i = 1 / A_ii, and rho = max_i sum_j |A_ij| / A_ii (Gershgorin bound of the spectral radius
@@ -95,27 +66,7 @@ __global__ void norm_partial_sums_kernel(const double* __restrict__ partials, No
 __global__ void norm_finalize_sums_kernel(const double* __restrict__ sums, int K, CycleControl* ctl, double* hist_res,
                                           double* hist_ms) {
     if (threadIdx.x != 0 || ctl->done) return;
-    double residue = 0.0;
-    bool diverged = false;
-    if (ctl->criterion == 3) {
-        double tot = 0.0;
-        for (int k = 0; k < K; ++k) tot += sums[2 * k];
-        residue = sqrt(tot);
-        diverged = !(residue <= 1.7976931348623157e308);
-    } else {
-        for (int k = 0; k < K; ++k) {
-            const double rk = sqrt(sums[2 * k] / sums[2 * k + 1]);
-            if (k == 0 || rk > residue || rk != rk) residue = rk;
-            if (!(rk <= 1.7976931348623157e308) && sums[2 * k + 1] > 0.0) diverged = true;
-        }
-    }
-    ctl->residue = residue;
-    if (diverged) ctl->error |= 2;
-    const int it = ctl->iter;
-    hist_res[it] = residue;
-    hist_ms[it] = (double)(global_timer_ns() - ctl->t_start_ns) * 1e-6;
-    ctl->iter = it + 1;
-    ctl->done = !((residue > ctl->tol) && (it + 1 < ctl->max_iter));
+    apply_stopping_rule(sums, K, ctl, hist_res, hist_ms, 1, 0);
 }
 
 template <typename T>

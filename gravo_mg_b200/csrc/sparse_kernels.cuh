@@ -43,6 +43,41 @@ struct CycleControl {
     int n_cols;
 };
 
+#ifdef __CUDACC__
+// Stopping rule of the cycle loop (multigrid_solver.cpp:1228-1277 norms, :1413-1417 loop test) from
+// the 2K sums {sum w r^2, sum w b^2} per right-hand side; one thread. record = 0: only the residue.
+__device__ inline void apply_stopping_rule(const double* sums, int K, CycleControl* ctl, double* hist_res, double* hist_ms,
+                                           int record, unsigned long long cond_handle) {
+    double residue = 0.0;
+    bool diverged = false;
+    if (ctl->criterion == 3) {
+        double tot = 0.0;
+        for (int k = 0; k < K; ++k) tot += sums[2 * k];
+        residue = sqrt(tot);
+        diverged = !(residue <= 1.7976931348623157e308);
+    } else {
+        for (int k = 0; k < K; ++k) {  // maxCoeff over the right-hand sides
+            const double rk = sqrt(sums[2 * k] / sums[2 * k + 1]);
+            if (k == 0 || rk > residue || rk != rk) residue = rk;
+            // 0/0 (an all-zero right-hand side) is NaN upstream too and simply ends the loop;
+            // a non-finite residual of a non-zero system means the smoother diverged
+            if (!(rk <= 1.7976931348623157e308) && sums[2 * k + 1] > 0.0) diverged = true;
+        }
+    }
+    ctl->residue = residue;
+    if (diverged) ctl->error |= 2;
+    if (record) {
+        const int it = ctl->iter;
+        hist_res[it] = residue;
+        hist_ms[it] = (double)(global_timer_ns() - ctl->t_start_ns) * 1e-6;
+        ctl->iter = it + 1;
+        const int keep_going = (residue > ctl->tol) && (it + 1 < ctl->max_iter);
+        ctl->done = !keep_going;
+        if (cond_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, keep_going ? 1u : 0u);
+    }
+}
+#endif
+
 template <typename T>
 struct SpmvArgs {
     int n_rows = 0;                    // direct path: rows [row_begin, n_rows) are processed

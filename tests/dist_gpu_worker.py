@@ -30,17 +30,26 @@ def main():
         single = gravomg.MultigridSolver(V, neigh, M, **kw)
         single.solver.set_option("lanes", 1)
         x1 = single.solve(lhs, rhs)
-        sharded = gravomg.MultigridSolver(V, neigh, M, **kw)
-        sharded.solver.set_option("lanes", 1)
-        sharded.distribute(replicate_rows=replicate_rows)
-        xs = sharded.solve(lhs, rhs)
+        # exchange variants: NVLink peer-memory pushes (default) under the host loop and inside the
+        # device-side while-graph, and the NCCL send/recv path; all must give the single-GPU bits
+        variants = {}
+        for vname, (p2p, loop_mode) in {"p2p_host_loop": (1, 0), "p2p_while_graph": (1, 1), "nccl": (0, 0)}.items():
+            sharded = gravomg.MultigridSolver(V, neigh, M, **kw)
+            sharded.solver.set_option("lanes", 1)
+            sharded.solver.set_option("p2p", p2p)
+            sharded.solver.set_option("loop_mode", loop_mode)
+            sharded.distribute(replicate_rows=replicate_rows)
+            xs = sharded.solve(lhs, rhs)
+            xs2 = sharded.solve(lhs, rhs)  # repeated solve on the staged pattern
+            variants[vname] = bool(np.array_equal(x1, xs)) and bool(np.array_equal(xs, xs2)) and \
+                sharded.solver_timing["iterations"] == single.solver_timing["iterations"]
         levels = [sharded.solver.dist_ranges(k) for k in range(len(single.prolongation_matrices) + 1)]
         m = M.diagonal()
         res = float(np.sqrt(((lhs @ xs - rhs) ** 2 * m[:, None]).sum(0) / ((rhs ** 2) * m[:, None]).sum(0)).max())
         out[name] = {
             "iters_single": single.solver_timing["iterations"], "iters_sharded": sharded.solver_timing["iterations"],
             "bitwise_equal": bool(np.array_equal(x1, xs)), "max_abs_diff": float(np.abs(x1 - xs).max()),
-            "residual": res, "residue_reported": sharded.solver_timing["residue"],
+            "variants": variants, "residual": res, "residue_reported": sharded.solver_timing["residue"],
             "sharded_levels": [int(not rep) for _, rep in levels], "rows": [int(r[-1]) for r, _ in levels],
         }
         # all ranks hold the same full solution

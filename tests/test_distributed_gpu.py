@@ -35,6 +35,6 @@ def test_sharded_solve_equals_single_gpu_solve():
             assert sum(r["sharded_levels"]) >= 1, (name, r)
             assert r["iters_single"] == r["iters_sharded"], (name, r)
             # per-row arithmetic does not depend on the partition: identical iterates (P4)
-            assert r["bitwise_equal"], (name, r)
+            assert r["bitwise_equal"] and all(r["variants"].values()), (name, r)
             assert r["residual"] <= 1e-6 and r["same_on_all_ranks"], (name, r)
     assert sum(per_rank[0]["two_sharded_levels"]["sharded_levels"]) == 2
