@@ -35,6 +35,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# NCCL prints its version banner to stdout by default; stdout carries exactly one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import numpy as np  # noqa: E402
 
 METRIC = "V-cycles/sec, 1M-vertex torus Poisson solve to 1e-6 M-norm residual"

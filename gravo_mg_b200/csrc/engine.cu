@@ -786,6 +786,7 @@ private:
     bool use_p2p() const { return st_->dist.world > 1 && st_->p2p; }
 
     void allocate_vectors() {
+        norm_sums_.ensure(2 * kMaxRhsTile * kMaxNormChunks);  // also the scratch word of box_barrier()
         release_peer_arena();
         if (use_p2p()) {
             build_peer_arena();
@@ -797,7 +798,6 @@ private:
         }
         rhs64_.ensure((size_t)st_->n * K_);
         if (max_halo_ && !use_p2p()) halo_send_.ensure(max_halo_ * K_), halo_recv_.ensure(max_halo_ * K_);
-        norm_sums_.ensure(2 * kMaxRhsTile * kMaxNormChunks);
         if (sizeof(T) == 4) {
             x64_.ensure((size_t)st_->n * K_);
             const size_t nc = (size_t)lv_[n_levels_].n * K_;
@@ -855,6 +855,7 @@ private:
     }
 
     void box_barrier() {
+        GMG_CUDA(cudaMemsetAsync(norm_sums_.ptr, 0, sizeof(double), stream_));
         GMG_NCCL(nccl().AllReduce(norm_sums_.ptr, norm_sums_.ptr, 1, ncclDouble, ncclSum, comm_, stream_));
         GMG_CUDA(cudaStreamSynchronize(stream_));
     }
