@@ -29,6 +29,9 @@ struct DevMat {
     int rows = 0, cols = 0;
     int64_t nnz = 0;
     DeviceBuffer<int> indptr, indices, rowidx;
+    DeviceBuffer<long long> pair_off;   // product plan of the Galerkin step that fills this matrix
+    DeviceBuffer<int2> pairs;           //   (sparse_kernels.h, build_spgemm_plan); empty: search per solve
+    bool planned = false;
     DeviceBuffer<int4> tiles;
     DeviceBuffer<double> v64;
     DeviceBuffer<float> v32;
@@ -371,10 +374,16 @@ public:
         for (int k = 0; k < L; ++k) {
             Level& f = lv_[k];
             Level& c = lv_[k + 1];
-            launch_spgemm_numeric(f.AP.nnz, f.AP.rowidx.ptr, f.AP.indices.ptr, f.AP.v64.ptr, f.A.indptr.ptr, f.A.indices.ptr,
-                                  f.A.v64.ptr, f.P.indptr.ptr, f.P.indices.ptr, f.P.v64.ptr, stream_);
-            launch_spgemm_numeric(c.A.nnz, c.A.rowidx.ptr, c.A.indices.ptr, c.A.v64.ptr, f.R.indptr.ptr, f.R.indices.ptr,
-                                  f.R.v64.ptr, f.AP.indptr.ptr, f.AP.indices.ptr, f.AP.v64.ptr, stream_);
+            if (f.AP.planned)
+                launch_spgemm_planned(f.AP.nnz, f.AP.pair_off.ptr, f.AP.pairs.ptr, f.A.v64.ptr, f.P.v64.ptr, f.AP.v64.ptr, stream_);
+            else
+                launch_spgemm_numeric(f.AP.nnz, f.AP.rowidx.ptr, f.AP.indices.ptr, f.AP.v64.ptr, f.A.indptr.ptr, f.A.indices.ptr,
+                                      f.A.v64.ptr, f.P.indptr.ptr, f.P.indices.ptr, f.P.v64.ptr, stream_);
+            if (c.A.planned)
+                launch_spgemm_planned(c.A.nnz, c.A.pair_off.ptr, c.A.pairs.ptr, f.R.v64.ptr, f.AP.v64.ptr, c.A.v64.ptr, stream_);
+            else
+                launch_spgemm_numeric(c.A.nnz, c.A.rowidx.ptr, c.A.indices.ptr, c.A.v64.ptr, f.R.indptr.ptr, f.R.indices.ptr,
+                                      f.R.v64.ptr, f.AP.indptr.ptr, f.AP.indices.ptr, f.AP.v64.ptr, stream_);
             launches += 2;
             if (k + 1 < L) {
                 launch_extract_dinv<T>(c.n, c.A.indptr.ptr, c.A.indices.ptr, c.A.v64.ptr, c.dinv.ptr, rho_.ptr + k + 1, ctl_.ptr,
@@ -678,6 +687,22 @@ private:
             lv_[k].A.make_plan(st_->a_pat[k].indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e);
             lv_[k].dinv.ensure(std::max(lv_[k].n, 1));
         }
+        // Galerkin product plans (once per pattern): which value pairs make up every entry of
+        // A_k U_k and of U_k^T (A_k U_k). Skipped above a memory budget (the search kernel remains).
+        long long plan_pairs = 0;
+        for (int k = 0; k < n_levels_; ++k) {
+            Level& f = lv_[k];
+            Level& c = lv_[k + 1];
+            f.AP.planned = c.A.planned = false;
+            if (!st_->spgemm_plan || plan_pairs > st_->spgemm_plan_max_pairs) continue;
+            plan_pairs += build_spgemm_plan(f.AP.nnz, f.AP.rowidx.ptr, f.AP.indices.ptr, f.A.indptr.ptr, f.A.indices.ptr,
+                                            f.P.indptr.ptr, f.P.indices.ptr, f.AP.pair_off, f.AP.pairs, stream_);
+            f.AP.planned = true;
+            plan_pairs += build_spgemm_plan(c.A.nnz, c.A.rowidx.ptr, c.A.indices.ptr, f.R.indptr.ptr, f.R.indices.ptr,
+                                            f.AP.indptr.ptr, f.AP.indices.ptr, c.A.pair_off, c.A.pairs, stream_);
+            c.A.planned = true;
+        }
+        st_->transfer_timing["galerkin_plan_pairs"] = (double)plan_pairs;
         upload_halos();
         coarse_.setup(lv_[n_levels_].n, stream_);
         GMG_CUDA(cudaStreamSynchronize(stream_));

@@ -54,6 +54,8 @@ struct SolverState {
                                      // false: pack / ncclSend / ncclRecv / unpack and ncclAllReduce
     bool fuse_norm = true;           // stopping test fused with the next cycle's first sweep
     bool use_pdl = true;             // programmatic dependent launch of the row-product kernels
+    bool spgemm_plan = true;         // Galerkin products from index-pair lists built once per pattern
+    long long spgemm_plan_max_pairs = 1500000000ll;  // 12 GB of pairs; beyond it levels fall back to the searching kernel
     int xfer_threads = -1;           // host threads staging caller buffers through pinned chunks (host_xfer.h);
                                      // -1 = min(8, cores / 2), 0 = plain pageable cudaMemcpyAsync
     // ---- symbolic phase (host): patterns of every level operator for the staged lhs pattern

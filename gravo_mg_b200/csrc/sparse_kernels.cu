@@ -1,5 +1,6 @@
 #include "sparse_kernels.h"
 
+#include <cub/device/device_scan.cuh>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -177,6 +178,55 @@ __global__ void spgemm_numeric_kernel(int64_t nnz_c, const int* __restrict__ c_r
                 hi = mid;
         }
         if (lo < end && b_col[lo] == j) s += a_val[p] * b_val[lo];
+    }
+    c_val[e] = s;
+}
+
+// Product plan of C = A * B on the fixed pattern of C: for every stored entry e = (i, j) of C the
+// list of (index into A's values, index into B's values) whose products make it up, in the order
+// of A's row i. Built once per sparsity pattern with the same search the per-solve kernel used to
+// repeat; the per-solve numeric product is then a gather-multiply-add without any search.
+// MODE 0: count the pairs of every entry; MODE 1: write them at offsets[e].
+template <int MODE>
+__global__ void spgemm_pairs_kernel(int64_t nnz_c, const int* __restrict__ c_rowidx, const int* __restrict__ c_col,
+                                    const int* __restrict__ a_ptr, const int* __restrict__ a_col,
+                                    const int* __restrict__ b_ptr, const int* __restrict__ b_col,
+                                    long long* __restrict__ offsets, int2* __restrict__ pairs) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nnz_c) return;
+    const int i = c_rowidx[e];
+    const int j = c_col[e];
+    long long at = MODE ? offsets[e] : 0;
+    for (int p = a_ptr[i]; p < a_ptr[i + 1]; ++p) {
+        const int k = a_col[p];
+        int lo = b_ptr[k];
+        const int end = b_ptr[k + 1];
+        int hi = end;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (b_col[mid] < j)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        if (lo < end && b_col[lo] == j) {
+            if (MODE) pairs[at] = make_int2(p, lo);
+            ++at;
+        }
+    }
+    if (!MODE) offsets[e] = at;
+}
+
+__global__ void spgemm_planned_kernel(int64_t nnz_c, const long long* __restrict__ offsets, const int2* __restrict__ pairs,
+                                      const double* __restrict__ a_val, const double* __restrict__ b_val,
+                                      double* __restrict__ c_val) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= nnz_c) return;
+    const long long t0 = offsets[e], t1 = offsets[e + 1];
+    double s = 0.0;
+    for (long long t = t0; t < t1; ++t) {
+        const int2 pr = __ldg(pairs + t);
+        s += a_val[pr.x] * b_val[pr.y];  // same order as the searching kernel: bit-identical sums
     }
     c_val[e] = s;
 }
@@ -421,6 +471,37 @@ void launch_spgemm_numeric(int64_t nnz_c, const int* c_rowidx, const int* c_col,
                                                                 b_col, b_val);
     GMG_CUDA(cudaGetLastError());
 }
+long long build_spgemm_plan(int64_t nnz_c, const int* c_rowidx, const int* c_col, const int* a_ptr, const int* a_col,
+                            const int* b_ptr, const int* b_col, DeviceBuffer<long long>& offsets, DeviceBuffer<int2>& pairs,
+                            cudaStream_t stream) {
+    offsets.ensure((size_t)nnz_c + 1);
+    GMG_CUDA(cudaMemsetAsync(offsets.ptr, 0, ((size_t)nnz_c + 1) * sizeof(long long), stream));
+    if (nnz_c <= 0) return 0;
+    const unsigned blocks = (unsigned)((nnz_c + 255) / 256);
+    spgemm_pairs_kernel<0><<<blocks, 256, 0, stream>>>(nnz_c, c_rowidx, c_col, a_ptr, a_col, b_ptr, b_col, offsets.ptr, nullptr);
+    GMG_CUDA(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    GMG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, offsets.ptr, offsets.ptr, (int64_t)nnz_c + 1, stream));
+    DeviceBuffer<unsigned char> tmp;
+    tmp.ensure(tmp_bytes);
+    GMG_CUDA(cub::DeviceScan::ExclusiveSum(tmp.ptr, tmp_bytes, offsets.ptr, offsets.ptr, (int64_t)nnz_c + 1, stream));
+    long long total = 0;
+    GMG_CUDA(cudaMemcpyAsync(&total, offsets.ptr + nnz_c, sizeof total, cudaMemcpyDeviceToHost, stream));
+    GMG_CUDA(cudaStreamSynchronize(stream));
+    pairs.ensure((size_t)std::max<long long>(total, 1));
+    spgemm_pairs_kernel<1><<<blocks, 256, 0, stream>>>(nnz_c, c_rowidx, c_col, a_ptr, a_col, b_ptr, b_col, offsets.ptr, pairs.ptr);
+    GMG_CUDA(cudaGetLastError());
+    GMG_CUDA(cudaStreamSynchronize(stream));  // `tmp` is a local
+    return total;
+}
+
+void launch_spgemm_planned(int64_t nnz_c, const long long* offsets, const int2* pairs, const double* a_val,
+                           const double* b_val, double* c_val, cudaStream_t stream) {
+    if (nnz_c <= 0) return;
+    spgemm_planned_kernel<<<(unsigned)((nnz_c + 255) / 256), 256, 0, stream>>>(nnz_c, offsets, pairs, a_val, b_val, c_val);
+    GMG_CUDA(cudaGetLastError());
+}
+
 void launch_csr_to_dense(int n, const int* rowptr, const int* colidx, const double* vals, double* dense, int lda,
                          cudaStream_t stream) {
     if (n <= 0) return;

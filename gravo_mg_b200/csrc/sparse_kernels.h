@@ -75,6 +75,15 @@ void launch_expand_rows(int n_rows, const int* rowptr, int* rowidx, cudaStream_t
 void launch_spgemm_numeric(int64_t nnz_c, const int* c_rowidx, const int* c_col, double* c_val, const int* a_ptr,
                            const int* a_col, const double* a_val, const int* b_ptr, const int* b_col,
                            const double* b_val, cudaStream_t stream);
+// The same product with the search done once per sparsity pattern: build_spgemm_plan records, for
+// every stored entry of C, the (A value, B value) index pairs whose products it sums (in the order
+// of A's row); launch_spgemm_planned is then a plain gather-multiply-add, bit-identical to
+// launch_spgemm_numeric. Returns the number of pairs.
+long long build_spgemm_plan(int64_t nnz_c, const int* c_rowidx, const int* c_col, const int* a_ptr, const int* a_col,
+                            const int* b_ptr, const int* b_col, DeviceBuffer<long long>& offsets, DeviceBuffer<int2>& pairs,
+                            cudaStream_t stream);
+void launch_spgemm_planned(int64_t nnz_c, const long long* offsets, const int2* pairs, const double* a_val,
+                           const double* b_val, double* c_val, cudaStream_t stream);
 void launch_csr_to_dense(int n, const int* rowptr, const int* colidx, const double* vals, double* dense, int lda,
                          cudaStream_t stream);
 

@@ -146,6 +146,26 @@ def test_p1_galerkin_operators(ico_small):
     assert [lv["nnz_u"] for lv in info[:-1]] == [u.nnz for u in p.U]
 
 
+def test_p1_galerkin_product_plans_are_bit_identical(ico10k, torus_mid):
+    """The per-pattern index-pair lists (build_spgemm_plan) replace the search of the per-solve
+    Galerkin kernels; the products are summed in the same order, so every level operator has the
+    same bits either way."""
+    for p in (ico10k, torus_mid):
+        mats = []
+        for plan in (1, 0):
+            s = p.new_solver().solver
+            s.set_option("spgemm_plan", plan)
+            s.stage(p.lhs, p.rhs)
+            s.solve_staged()
+            mats.append(_device_levels(s, len(p.U)))
+            if plan:
+                assert s.transfer_timing()["galerkin_plan_pairs"] > 0
+        for a, b in zip(*mats):
+            np.testing.assert_array_equal(a.indptr, b.indptr)
+            np.testing.assert_array_equal(a.indices, b.indices)
+            np.testing.assert_array_equal(a.data, b.data)
+
+
 def test_p1_coarse_solve(ico_small):
     """Dense Cholesky + explicit inverse on the device vs the oracle's sparse LDL^T."""
     p = ico_small
