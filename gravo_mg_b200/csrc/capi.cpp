@@ -159,6 +159,7 @@ int gmg_set_option(gmg_handle h, const char* key, double value) {
         else if (k == "xfer_threads") s.xfer_threads = (int)value;
         else if (k == "p2p") s.p2p = value != 0.0, hierarchy = true;
         else if (k == "spgemm_plan") s.spgemm_plan = value != 0.0, hierarchy = true;
+        else if (k == "coarse_dataflow") s.coarse_dataflow = value != 0.0, cycle = true;
         else throw std::invalid_argument("unknown option: " + k);
         require(s.params.pre_iters >= 0 && s.params.post_iters >= 0 && s.params.pre_iters <= 16 && s.params.post_iters <= 16, "sweep counts must be 0..16");
         require(s.params.smoother == GMG_SMOOTHER_JACOBI || s.params.smoother == GMG_SMOOTHER_CHEBYSHEV, "unknown smoother");
@@ -197,6 +198,7 @@ int gmg_get_option(gmg_handle h, const char* key, double* value) {
         else if (k == "xfer_threads") *value = s.xfer_threads;
         else if (k == "p2p") *value = s.p2p;
         else if (k == "spgemm_plan") *value = s.spgemm_plan;
+        else if (k == "coarse_dataflow") *value = s.coarse_dataflow;
         else throw std::invalid_argument("unknown option: " + k);
     });
 }

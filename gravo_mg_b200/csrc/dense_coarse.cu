@@ -2,6 +2,7 @@
 
 #include <algorithm>
 
+#include "dense_factor.cuh"
 #include "sparse_kernels.h"
 
 namespace gmg {
@@ -375,6 +376,26 @@ void DenseCoarseSolver::setup(int n, cudaStream_t stream) {
         second.count = (int)tasks.size() - second.first;
         inv_second_.push_back(second);
     }
+    // dataflow factorisation (dense_factor.cuh): tiles in dependency order — Cholesky column c, then
+    // the inverse tiles of row c (they need L(c, .) and W_cc, all final once column c is done)
+    std::vector<FactorTask> ftasks;
+    for (int c = 0; c < nb_; ++c) {
+        for (int i = c; i < nb_; ++i) ftasks.push_back({0, i, c});
+        for (int j = 0; j < c; ++j) ftasks.push_back({1, c, j});
+    }
+    n_ftasks_ = (int)ftasks.size();
+    ftasks_.ensure(ftasks.size() * sizeof(FactorTask));
+    GMG_CUDA(cudaMemcpyAsync(ftasks_.ptr, ftasks.data(), ftasks.size() * sizeof(FactorTask), cudaMemcpyHostToDevice, stream));
+    fflags_.ensure((size_t)2 * nb_ * nb_ + nb_ + 1);
+    GMG_CUDA(cudaMemsetAsync(fflags_.ptr, 0, fflags_.count * sizeof(unsigned), stream));
+    rdiag_.ensure(npad_);
+    GMG_CUDA(cudaFuncSetAttribute(dense_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactorSmem));
+    int sms = 0, dev = 0;
+    GMG_CUDA(cudaGetDevice(&dev));
+    GMG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int per_sm = 0;
+    GMG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dense_factor_kernel, 256, kFactorSmem));
+    factor_grid_ = std::max(1, std::min(n_ftasks_, sms * std::max(per_sm, 1)));
     tasks_.ensure(std::max<size_t>(tasks.size(), 1) * sizeof(GemmTask));
     if (!tasks.empty())
         GMG_CUDA(cudaMemcpyAsync(tasks_.ptr, tasks.data(), tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice, stream));
@@ -399,12 +420,40 @@ void DenseCoarseSolver::factor(const int* rowptr, const int* colidx, const doubl
     };
     mark(0);
     GMG_CUDA(cudaMemsetAsync(L_.ptr, 0, bytes, stream));
-    GMG_CUDA(cudaMemsetAsync(W_.ptr, 0, bytes, stream));
+    if (!dataflow_) GMG_CUDA(cudaMemsetAsync(W_.ptr, 0, bytes, stream));
     launch_csr_to_dense(n_, rowptr, colidx, vals, L_.ptr, ld, stream);
     ++launches;
     if (npad_ > n_) {
         pad_identity_kernel<<<(npad_ - n_ + 63) / 64, 64, 0, stream>>>(L_.ptr, ld, n_, npad_);
         ++launches;
+    }
+    if (dataflow_) {
+        // one kernel: tiles of L, W = L^-1 and W^T as tasks ordered by per-tile flags (dense_factor.cuh)
+        FactorArgs fa;
+        fa.L = L_.ptr, fa.W = W_.ptr, fa.Wt = Wt_.ptr, fa.rdiag = rdiag_.ptr, fa.ld = ld, fa.nb = nb_;
+        fa.tasks = reinterpret_cast<const FactorTask*>(ftasks_.ptr), fa.n_tasks = n_ftasks_;
+        fa.next = fflags_.ptr;
+        fa.flag_l = fflags_.ptr + 1, fa.flag_x = fa.flag_l + (size_t)nb_ * nb_, fa.flag_w = fa.flag_x + (size_t)nb_ * nb_;
+        fa.epoch = ++epoch_;
+        if (epoch_ == 0) fa.epoch = ++epoch_;  // flags start at 0
+        fa.ctl = ctl;
+        GMG_CUDA(cudaMemsetAsync(fflags_.ptr, 0, sizeof(unsigned), stream));
+        mark(1);
+        dense_factor_kernel<<<factor_grid_, 256, kFactorSmem, stream>>>(fa);
+        GMG_CUDA(cudaGetLastError());
+        ++launches;
+        mark(6);
+        factor_launches_ = launches;
+        if (profile) {
+            GMG_CUDA(cudaStreamSynchronize(stream));
+            float ms0 = 0, ms1 = 0;
+            GMG_CUDA(cudaEventElapsedTime(&ms0, ev[0], ev[1]));
+            GMG_CUDA(cudaEventElapsedTime(&ms1, ev[1], ev[2]));
+            std::fprintf(stderr, "[gravomg_b200] coarse factor n=%d (dataflow, %d tile tasks, grid %d): densify %.1f us, factor + inverse %.1f us\n",
+                         n_, n_ftasks_, factor_grid_, 1e3 * ms0, 1e3 * ms1);
+            for (auto e : ev) cudaEventDestroy(e);
+        }
+        return;
     }
     const GemmTask* tasks = reinterpret_cast<const GemmTask*>(tasks_.ptr);
     for (int j = 0; j < nb_; ++j) {

@@ -24,6 +24,8 @@ public:
                 bool profile = false);
     // x = A^-1 b for K columns stored row-major with leading dimension ld. b and x may alias.
     void solve(const double* b, double* x, int K, int ld, const CycleControl* ctl, cudaStream_t stream);
+    // true (default): one dataflow kernel (dense_factor.cuh); false: one kernel per phase
+    void set_dataflow(bool on) { dataflow_ = on; }
     int size() const { return n_; }
     // factor storage for kernels that fuse the solve (tail_kernel.cuh): W = L^-1 (lower), Wt = W^T, scratch y
     const double* w() const { return W_.ptr; }
@@ -40,6 +42,12 @@ private:
     int factor_launches_ = 0;
     DeviceBuffer<double> L_, W_, Wt_, tmp_, y_;
     DeviceBuffer<unsigned char> tasks_;  // GemmTask array
+    DeviceBuffer<unsigned char> ftasks_; // FactorTask array of the dataflow kernel
+    DeviceBuffer<unsigned> fflags_;      // task counter + per-tile flags
+    DeviceBuffer<double> rdiag_;
+    int n_ftasks_ = 0, factor_grid_ = 1;
+    unsigned epoch_ = 0;
+    bool dataflow_ = true;
     std::vector<Batch> chol_panel_, chol_update_;  // per block column
     std::vector<Batch> inv_first_, inv_second_;    // per doubling level
 };

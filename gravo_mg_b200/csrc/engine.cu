@@ -314,6 +314,7 @@ public:
         solved_ = true;
         if (ctl_host_->error & 1) throw std::runtime_error("an operator has a missing, non-positive or non-finite diagonal entry (Jacobi smoother needs A_ii > 0)");
         if (ctl_host_->error & 4) throw std::runtime_error("coarsest-level Cholesky broke down: the Galerkin operator is not positive definite");
+        if (ctl_host_->error & 16) throw std::runtime_error("coarsest-level factorisation stalled waiting for a tile (internal error)");
         if (ctl_host_->error & 8) throw std::runtime_error("multi-GPU halo exchange timed out waiting for a peer rank (ranks out of step, or a peer failed)");
         if (ctl_host_->error & 2) throw std::runtime_error("residual became non-finite (diverged); try a smaller omega");
     }
@@ -398,6 +399,7 @@ public:
             ++launches;
         }
         if (after_reduction) GMG_CUDA(cudaEventRecord(after_reduction, stream_));
+        coarse_.set_dataflow(st_->coarse_dataflow);
         coarse_.factor(lv_[L].A.indptr.ptr, lv_[L].A.indices.ptr, lv_[L].A.v64.ptr, ctl_.ptr, stream_, st_->profile);
         launches += coarse_.launches_per_factor();
         numeric_ready_ = true;
@@ -421,6 +423,7 @@ public:
         GMG_CUDA(cudaStreamSynchronize(stream_));
         if (ctl_host_->error & 1) throw std::runtime_error("an operator has a missing, non-positive or non-finite diagonal entry (Jacobi smoother needs A_ii > 0)");
         if (ctl_host_->error & 4) throw std::runtime_error("coarsest-level Cholesky broke down: the Galerkin operator is not positive definite");
+        if (ctl_host_->error & 16) throw std::runtime_error("coarsest-level factorisation stalled waiting for a tile (internal error)");
     }
 
     // ------------------------------------------------------------------ single operators

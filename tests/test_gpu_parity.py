@@ -189,6 +189,37 @@ def test_p1_coarse_solve(ico_small):
     assert backward <= 1e-13
 
 
+@pytest.mark.parametrize("fixture,expect_rows", [("ico_small", 54), ("ico10k", 1800), ("torus_mid", 2700)])
+def test_p1_coarse_factor_dataflow_kernel(request, fixture, expect_rows):
+    """The coarse factor as one dataflow kernel (tiles + flags, dense_factor.cuh) against the
+    kernel-per-phase version and against numpy on the device's own coarse operator: one tile
+    (54 rows), ~29 and ~43 tile rows (more tasks than resident CTAs)."""
+    p = request.getfixturevalue(fixture)
+    L = len(p.U)
+    nc = p.U[-1].shape[1]
+    assert 0.5 * expect_rows <= nc <= 1.6 * expect_rows
+    rng = np.random.default_rng(5)
+    b = rng.standard_normal((nc, 3))
+    lhs = (p.M + 1e-3 * p.S).tocsr()
+    got = {}
+    for flag in (1, 0):
+        s, _, _ = _staged(p, 3, lhs=lhs)
+        s.set_option("coarse_dataflow", flag)
+        got[flag] = s.level_op("coarse", L, b)
+        got[flag, "again"] = s.level_op("coarse", L, b)   # second factorisation: next flag epoch
+        Ac = s.level_matrix(L).toarray()
+    want = np.linalg.solve(Ac, b)
+    for flag in (1, 0):
+        assert np.linalg.norm(got[flag] - want) <= 1e-11 * np.linalg.norm(want), flag
+        np.testing.assert_array_equal(got[flag], got[flag, "again"])
+    # Poisson (nearly singular operator): backward error of the dataflow factor
+    s, _, _ = _staged(p, 3)
+    x = s.level_op("coarse", L, b)
+    Ac = s.level_matrix(L).toarray()
+    backward = np.linalg.norm(Ac @ x - b) / (np.linalg.norm(Ac, 2) * np.linalg.norm(x) + np.linalg.norm(b))
+    assert backward <= 1e-13
+
+
 def test_smoother_weights_are_chebyshev_roots_on_the_gershgorin_band(ico_small):
     p = ico_small
     s, lhs, _ = _staged(p, 1, pre_iters=3, post_iters=2, cheb_alpha=8.0)
