@@ -51,6 +51,14 @@ struct FactorArgs {
     CycleControl* ctl;
 };
 
+// Optional per-task timeline for tools/factor_lab.cu (claim, inputs ready, tile posted, task end).
+#ifdef GMG_FACTOR_TRACE
+__device__ unsigned long long g_ftrace[8192][4];
+#define FTRACE(task, slot) do { if (threadIdx.x == 0 && (task) < 8192) g_ftrace[task][slot] = global_timer_ns(); } while (0)
+#else
+#define FTRACE(task, slot) do { } while (0)
+#endif
+
 constexpr size_t kFactorSmem = (3 * (size_t)FB * FS + 2 * (size_t)FB * FPS + 2 * FB) * sizeof(double) + 16;
 
 __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
@@ -303,6 +311,7 @@ __global__ void __launch_bounds__(256) dense_factor_kernel(const FactorArgs f) {
         if (t >= f.n_tasks) break;
         const FactorTask task = f.tasks[t];
         const int i = task.i, j = task.j;
+        FTRACE(t, 0);
         double acc[4][4];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
@@ -320,6 +329,7 @@ __global__ void __launch_bounds__(256) dense_factor_kernel(const FactorArgs f) {
                 mma_tile(acc, As, Bs, tx, ty);
                 __syncthreads();
             }
+            FTRACE(t, 1);
             double* Aij = tile(f.L, i, j);
             double a[4][4];
 #pragma unroll
@@ -340,6 +350,7 @@ __global__ void __launch_bounds__(256) dense_factor_kernel(const FactorArgs f) {
                 __syncthreads();  // rd[] complete (written during the panels), As complete
                 if (tid < FB) f.rdiag[FB * j + tid] = rd[tid];
                 post_tile(&f.flag_l[j * nb + j], f.epoch);
+                FTRACE(t, 2);
                 // W_jj = L_jj^-1: needed by the inverse tiles only, so after L_jj is published
                 tri_inverse_tile(As, Bs, Ts, dd);
                 double* Wjj = tile(f.W, j, j);
@@ -350,8 +361,10 @@ __global__ void __launch_bounds__(256) dense_factor_kernel(const FactorArgs f) {
                     Wtjj[row + (size_t)col * ld] = col >= row ? Bs[col][row] : 0.0;
                 }
                 post_tile(&f.flag_w[j], f.epoch);
+                FTRACE(t, 3);
             } else {
                 wait_tile(&f.flag_l[j * nb + j], f.epoch, f.ctl);
+                FTRACE(t, 2);
                 load_tile_rows(Ts, tile(f.L, j, j), ld);
                 if (tid < FB) rd[tid] = __ldcg(f.rdiag + FB * j + tid);
                 __syncthreads();
@@ -361,6 +374,7 @@ __global__ void __launch_bounds__(256) dense_factor_kernel(const FactorArgs f) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) Aij[(tx + 16 * r) + (size_t)(ty + 16 * c) * ld] = a[r][c];
                 post_tile(&f.flag_l[i * nb + j], f.epoch);
+                FTRACE(t, 3);
             }
         } else {
             // ---------------------------------------------------------------- inverse tile X(i, j), i > j
@@ -373,7 +387,9 @@ __global__ void __launch_bounds__(256) dense_factor_kernel(const FactorArgs f) {
                 mma_tile(acc, As, Bs, tx, ty);
                 __syncthreads();
             }
+            FTRACE(t, 1);
             wait_tile(&f.flag_w[i], f.epoch, f.ctl);
+            FTRACE(t, 2);
             load_tile_cols(As, tile(f.W, i, i), ld);
 #pragma unroll
             for (int r = 0; r < 4; ++r)
@@ -400,6 +416,7 @@ __global__ void __launch_bounds__(256) dense_factor_kernel(const FactorArgs f) {
                 Wtji[row + (size_t)col * ld] = Ts[col][row];
             }
             post_tile(&f.flag_x[i * nb + j], f.epoch);
+            FTRACE(t, 3);
         }
     }
 }
