@@ -719,6 +719,7 @@ private:
     struct DevHalo {
         std::vector<DeviceBuffer<int>> send_idx, recv_idx;  // per peer
         std::vector<int> n_send, n_recv;
+        DeviceBuffer<unsigned char> mask;  // per row of the exchanged vector: bit q = peer q gathers it (fused push)
     };
 
     void upload_halos() {
@@ -742,6 +743,12 @@ private:
                     tot_s += h.send[q].size(), tot_r += h.recv[q].size();
                 }
                 max_halo_ = std::max(max_halo_, std::max(tot_s, tot_r));
+                // rows of the exchanged vector: level k for A and R, level k + 1 for P
+                const int vec_level = hop == HALO_P ? k + 1 : k;
+                std::vector<unsigned char> m((size_t)std::max(lv_[vec_level].n, 1), 0);
+                for (int q = 0; q < d.world; ++q)
+                    for (int row : h.send[q]) m[row] |= (unsigned char)(1u << q);
+                dh.mask.upload(m, stream_);
             }
         }
         GMG_CUDA(cudaStreamSynchronize(stream_));  // the host lists may be rebuilt
@@ -879,6 +886,8 @@ private:
             GMG_CUDA(cudaIpcOpenMemHandle(&peer_base_[q], all[q], cudaIpcMemLazyEnablePeerAccess));
             fabric_.peer_delta[q] = static_cast<char*>(peer_base_[q]) - static_cast<char*>(arena_);
         }
+        fabric_dev_.ensure(1);
+        GMG_CUDA(cudaMemcpyAsync(fabric_dev_.ptr, &fabric_, sizeof fabric_, cudaMemcpyHostToDevice, stream_));
         box_barrier();  // nobody pushes before everybody has mapped everybody
     }
 
@@ -1070,6 +1079,7 @@ private:
             if (fused) op.args.dinv = lv_[0].dinv.ptr, op.args.omega_ptr = weight_ptr(0, false, 0), op.args.out = alt;
             ops_.push_back(op);
         }
+        if (use_p2p() && st_->p2p_fuse) fuse_exchanges();
         cycle_dirty_ = false;
         // one-time per-kernel attribute/occupancy calls must not land inside a stream capture
         set_launch_dry_run(true);
@@ -1083,6 +1093,63 @@ private:
             throw;
         }
         set_launch_dry_run(false);
+    }
+
+    // Multi-GPU: fold every halo push into the kernel that produces the vector (its epilogue also
+    // stores the rows peers gather into the peers' HBM and the last CTA signals) and the wait into
+    // the kernel that gathers it. A push stays a kernel of its own when producer or consumer is
+    // not a row-product kernel (all-gather into the first replicated level, memset, coarse solve).
+    void fuse_exchanges() {
+        auto writes = [](const Op& op, const T* v) {
+            if (op.kind == OP_ZERO) return op.zero_ptr == (const void*)v;
+            if (op.kind == OP_ALLGATHER) return op.vec == v || op.vec2 == v;
+            if (op.kind == OP_HALO || op.kind == OP_TAIL) return false;
+            if (op.kind == OP_COARSE) return false;  // writes the coarsest x, which is never exchanged
+            return op.args.out == v || op.args.out2 == v;
+        };
+        auto row_product = [](const Op& op) {
+            return op.plan != nullptr && (op.kind == OP_JACOBI || op.kind == OP_RESIDUAL || op.kind == OP_RESTRICT ||
+                                          op.kind == OP_PROLONG || op.kind == OP_NORM);
+        };
+        auto mark_producer = [&](Op& w, const T* v, const unsigned char* mask) {
+            if (w.args.send_mask && w.args.send_mask != mask) return false;
+            w.args.fabric = fabric_dev_.ptr, w.args.send_mask = mask, w.args.push_out2 = (w.args.out2 == v) ? 1 : 0;
+            return true;
+        };
+        for (size_t ih = 0; ih < ops_.size();) {
+            Op& h = ops_[ih];
+            if (h.kind != OP_HALO || ih + 1 >= ops_.size()) {
+                ++ih;
+                continue;
+            }
+            Op& c = ops_[ih + 1];
+            const T* v = h.vec;
+            const DevHalo& dh = halo_[h.halo_op][h.level];
+            bool ok = row_product(c) && c.args.x == v && dh.mask.ptr != nullptr;
+            // most recent writer of v: earlier in the cycle, else the end of the previous cycle (wrap)
+            int writer = -1;
+            bool wrapped = false;
+            for (int j = (int)ih - 1; ok && j >= 0 && writer < 0; --j)
+                if (writes(ops_[j], v)) writer = j;
+            for (int j = (int)ops_.size() - 1; ok && j > (int)ih && writer < 0; --j)
+                if (writes(ops_[j], v)) writer = j, wrapped = true;
+            if (ok && writer >= 0 && !(row_product(ops_[writer]) && ops_[writer].kind != OP_NORM) &&
+                !(ops_[writer].kind == OP_NORM && ops_[writer].epi == EPI_NORMJAC))
+                ok = false;
+            if (ok && writer >= 0) ok = mark_producer(ops_[writer], v, dh.mask.ptr);
+            if (ok && (writer < 0 || wrapped)) {
+                // first cycle of a solve: the prologue sweep (if it writes v) pushes; otherwise v is the
+                // initial guess, identical on every rank
+                for (Op& pr : prologue_)
+                    if (writes(pr, v) && !mark_producer(pr, v, dh.mask.ptr)) ok = false;
+            }
+            if (!ok) {
+                ++ih;
+                continue;
+            }
+            c.args.fabric = fabric_dev_.ptr, c.args.wait_peers = 1;
+            ops_.erase(ops_.begin() + ih);
+        }
     }
 
     int tail_grid() {
@@ -1380,6 +1447,7 @@ private:
     size_t arena_bytes_ = 0;
     void* peer_base_[kMaxPeers] = {};  // peers' arenas mapped into this process
     PeerFabric fabric_;
+    DeviceBuffer<PeerFabric> fabric_dev_;
     DeviceBuffer<unsigned long long> peer_local_;
     DeviceBuffer<unsigned char> ipc_buf_;
     bool hierarchy_ready_ = false, pattern_ready_ = false, staged_ = false, solved_ = false, cycle_dirty_ = true;

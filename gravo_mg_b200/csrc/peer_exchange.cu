@@ -3,20 +3,6 @@
 namespace gmg {
 namespace {
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-template <typename P>
-__device__ __forceinline__ P* on_peer(P* local, const PeerFabric& f, int q) {
-    return reinterpret_cast<P*>(reinterpret_cast<char*>(local) + f.peer_delta[q]);
-}
-
 // All blocks of the calling kernel have stored their data into peer memory. The last block to get
 // here publishes this rank's next epoch to every peer and waits until every peer has published
 // the same epoch (i.e. its stores into OUR arena are complete and visible).

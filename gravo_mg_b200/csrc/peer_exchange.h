@@ -22,28 +22,10 @@
 // only be one exchange ahead of any other, and consecutive exchanges never touch the same vector.
 // A spin that lasts longer than kPeerTimeoutNs sets CycleControl::error bit 8 instead of hanging.
 #pragma once
+#include "peer_fabric.cuh"
 #include "sparse_kernels.h"
 
 namespace gmg {
-
-constexpr int kMaxPeers = 8;
-constexpr int kPeerNormSlots = 2 * kMaxRhsTile * kMaxNormChunks;  // 2K doubles per rank
-constexpr unsigned long long kPeerTimeoutNs = 10000000000ull;  // 10 s: ranks drift by host work, never by this much
-
-// Mailbox at the start of every rank's arena (written by peers).
-struct PeerMailbox {
-    unsigned long long flags[kMaxPeers];                  // flags[q]: last epoch rank q has signalled
-    double norm[2][kMaxPeers][kPeerNormSlots];            // [epoch parity][source rank][2K sums]
-};
-
-// Per-rank view of the box, passed to the kernels by value.
-struct PeerFabric {
-    int rank = 0, world = 1;
-    PeerMailbox* box = nullptr;                           // local mailbox (arena offset 0)
-    long long peer_delta[kMaxPeers] = {0};                // peer arena base - local arena base, bytes
-    unsigned long long* epoch = nullptr;                  // local: exchanges completed so far
-    unsigned int* ticket = nullptr;                       // local: last-block detection
-};
 
 template <typename T>
 struct PeerPushArgs {

@@ -1,0 +1,75 @@
+// Peer-memory fabric of the multi-GPU V-cycle: what a kernel needs to store into a peer's HBM
+// and to signal / await an exchange (see peer_exchange.h for the protocol).
+#pragma once
+#include "common.cuh"
+
+namespace gmg {
+
+constexpr int kMaxPeers = 8;
+constexpr int kPeerNormSlots = 64;  // 2 sums x up to 32 right-hand sides per rank
+constexpr unsigned long long kPeerTimeoutNs = 10000000000ull;  // 10 s: ranks drift by host work, never by this much
+
+// Mailbox at the start of every rank's arena (written by peers).
+struct PeerMailbox {
+    unsigned long long flags[kMaxPeers];                  // flags[q]: last epoch rank q has signalled
+    double norm[2][kMaxPeers][kPeerNormSlots];            // [cycle parity][source rank][2K sums]
+};
+
+// Per-rank view of the box.
+struct PeerFabric {
+    int rank = 0, world = 1;
+    PeerMailbox* box = nullptr;                           // local mailbox (arena offset 0)
+    long long peer_delta[kMaxPeers] = {0};                // peer arena base - local arena base, bytes
+    unsigned long long* epoch = nullptr;                  // local: exchanges completed so far
+    unsigned int* ticket = nullptr;                       // local: last-block detection
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+template <typename P>
+__device__ __forceinline__ P* on_peer(P* local, const PeerFabric& f, int q) {
+    return reinterpret_cast<P*>(reinterpret_cast<char*>(local) + f.peer_delta[q]);
+}
+
+// Producer side of a fused exchange, called by ONE thread of every CTA after the CTA's threads
+// have fenced their peer stores and met at a barrier: the last CTA of the grid advances this
+// rank's epoch and publishes it to every peer.
+__device__ __forceinline__ void peer_signal_from_cta(const PeerFabric& f) {
+    __threadfence_system();
+    const unsigned t = atomicAdd(f.ticket, 1u);
+    if (t != gridDim.x - 1) return;
+    __threadfence_system();  // the other CTAs' stores (ordered before their tickets) before our flags
+    *f.ticket = 0;
+    const unsigned long long e = *f.epoch + 1;
+    *f.epoch = e;
+    for (int q = 0; q < f.world; ++q)
+        if (q != f.rank) st_release_sys(&on_peer(f.box, f, q)->flags[f.rank], e);
+}
+
+// Consumer side, called by a full warp: returns when every peer has signalled this rank's
+// current epoch, i.e. the rows peers pushed into the vector about to be gathered are in place.
+// `error` gets bit 8 after kPeerTimeoutNs (and stops later waits of the solve).
+__device__ __forceinline__ void peer_wait_warp(const PeerFabric& f, int* error) {
+    const int q = threadIdx.x & 31;
+    if (q < f.world && q != f.rank) {
+        const unsigned long long e = *const_cast<volatile unsigned long long*>(f.epoch);
+        const unsigned long long t0 = global_timer_ns();
+        while (!(*const_cast<volatile int*>(error) & 8) && ld_acquire_sys(&f.box->flags[q]) < e) {
+            if (global_timer_ns() - t0 > kPeerTimeoutNs) {
+                atomicOr(error, 8);
+                break;
+            }
+        }
+    }
+    __syncwarp();
+}
+#endif
+
+}  // namespace gmg

@@ -25,6 +25,7 @@
 //           used when a row does not fit a stage and as an independent cross-check.
 #pragma once
 #include "common.cuh"
+#include "peer_fabric.cuh"
 
 namespace gmg {
 
@@ -100,8 +101,32 @@ struct SpmvArgs {
     int n_tiles = 0;
     int stage_elems = 0;               // staged: capacity of one stage in entries (multiple of 4)
     int stage_rows = 0;                // staged: rows per tile (consumer threads / LANES)
-    const CycleControl* ctl = nullptr; // optional early-out
+    const CycleControl* ctl = nullptr; // loop state (error bits)
+    // multi-GPU, fused halo exchange (peer_exchange.h): rows of `out` (`out2` when push_out2) that
+    // peers gather are also stored into the peers' copies of the vector as they are produced, the
+    // last CTA signals the exchange; a consumer first waits for the peers' signal of the vector it gathers
+    const PeerFabric* fabric = nullptr;
+    const unsigned char* send_mask = nullptr;  // [rows of out] bit q: peer q needs this row
+    int push_out2 = 0;
+    int wait_peers = 0;
 };
+
+#ifdef __CUDACC__
+template <typename T, int K>
+__device__ __forceinline__ void peer_push_row(const SpmvArgs<T>& a, T* vec, int row, const T (&v)[K]) {
+    unsigned m = a.send_mask[row];
+    if (!m) return;
+    const size_t o = (size_t)row * a.ld;
+    while (m) {
+        const int q = __ffs(m) - 1;
+        m &= m - 1;
+        T* pv = on_peer(vec, *a.fabric, q) + o;
+#pragma unroll
+        for (int k = 0; k < K; ++k) pv[k] = v[k];
+    }
+    __threadfence_system();  // before this CTA's end-of-kernel ticket
+}
+#endif
 
 constexpr int kStagedThreads = 256;
 constexpr int kStagedStages = 2;
@@ -162,23 +187,20 @@ template <typename T, int K, int EPI>
 __device__ __forceinline__ void row_epilogue(const SpmvArgs<T>& a, int row, const T (&acc)[K], const RowOperands<T, K>& r,
                                              double (&nrm)[2 * K]) {
     const size_t o = (size_t)row * a.ld;
+    T res[K];
     if (EPI == EPI_SPMV) {
 #pragma unroll
         for (int k = 0; k < K; ++k) a.out[o + k] = acc[k];
         if (a.out2) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) a.out2[o + k] = r.scale * acc[k];
+            for (int k = 0; k < K; ++k) res[k] = r.scale * acc[k];
+#pragma unroll
+            for (int k = 0; k < K; ++k) a.out2[o + k] = res[k];
+            if (a.send_mask && a.push_out2) peer_push_row<T, K>(a, a.out2, row, res);
         }
-    } else if (EPI == EPI_JACOBI) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) a.out[o + k] = r.xo[k] + r.scale * (r.b[k] - acc[k]);
-    } else if (EPI == EPI_RESIDUAL) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) a.out[o + k] = r.b[k] - acc[k];
-    } else if (EPI == EPI_ADD) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) a.out[o + k] = r.xo[k] + acc[k];
-    } else {  // EPI_NORM, EPI_NORMJAC
+        if (a.send_mask && !a.push_out2) peer_push_row<T, K>(a, a.out, row, acc);
+    }
+    if (EPI == EPI_NORM || EPI == EPI_NORMJAC) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const double bk = (double)r.b[k];
@@ -186,10 +208,17 @@ __device__ __forceinline__ void row_epilogue(const SpmvArgs<T>& a, int row, cons
             nrm[2 * k] += r.w * d * d;
             nrm[2 * k + 1] += r.w * bk * bk;
         }
-        if (EPI == EPI_NORMJAC) {
+    }
+    if (EPI != EPI_SPMV && EPI != EPI_NORM) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) a.out[o + k] = r.xo[k] + r.scale * (r.b[k] - acc[k]);
+        for (int k = 0; k < K; ++k) {
+            if (EPI == EPI_JACOBI || EPI == EPI_NORMJAC) res[k] = r.xo[k] + r.scale * (r.b[k] - acc[k]);
+            else if (EPI == EPI_RESIDUAL) res[k] = r.b[k] - acc[k];
+            else res[k] = r.xo[k] + acc[k];  // EPI_ADD
         }
+#pragma unroll
+        for (int k = 0; k < K; ++k) a.out[o + k] = res[k];
+        if (a.send_mask) peer_push_row<T, K>(a, a.out, row, res);
     }
 }
 
@@ -278,6 +307,7 @@ __global__ void __launch_bounds__(TPB + 32) spmv_staged_kernel(const SpmvArgs<T>
         // Vectors (x, b, out of the previous kernel) must not be touched before that kernel is done.
         grid_dependency_wait();
         grid_launch_dependents();
+        if (a.wait_peers) peer_wait_warp(*a.fabric, const_cast<int*>(&a.ctl->error));
         const int ctid = tid - 32;
         const int lane = ctid % LANES;
         for (int it = 0; it < n_my; ++it) {
@@ -325,6 +355,10 @@ __global__ void __launch_bounds__(TPB + 32) spmv_staged_kernel(const SpmvArgs<T>
         }
     }
     if (EPI == EPI_NORM || EPI == EPI_NORMJAC) block_sum_store<2 * K, TPB + 32>(nrm, a.partials + (size_t)blockIdx.x * 2 * K);
+    if (EPI != EPI_NORM && a.send_mask) {  // all rows of this CTA are stored (and fenced where pushed)
+        __syncthreads();
+        if (tid == 0) peer_signal_from_cta(*a.fabric);
+    }
 }
 
 // ---------------------------------------------------------------------------- direct path
@@ -333,6 +367,7 @@ __global__ void __launch_bounds__(kDirectThreads) spmv_direct_kernel(const SpmvA
     constexpr int TPB = kDirectThreads;
     grid_dependency_wait();
     grid_launch_dependents();
+    if (a.wait_peers) peer_wait_warp(*a.fabric, const_cast<int*>(&a.ctl->error));
     const int lane = threadIdx.x % LANES;
     const int rows_per_block = TPB / LANES;
     double nrm[2 * K];
@@ -368,6 +403,10 @@ __global__ void __launch_bounds__(kDirectThreads) spmv_direct_kernel(const SpmvA
         }
     }
     if (EPI == EPI_NORM || EPI == EPI_NORMJAC) block_sum_store<2 * K, TPB>(nrm, a.partials + (size_t)blockIdx.x * 2 * K);
+    if (EPI != EPI_NORM && a.send_mask) {
+        __syncthreads();
+        if (threadIdx.x == 0) peer_signal_from_cta(*a.fabric);
+    }
 }
 
 }  // namespace gmg

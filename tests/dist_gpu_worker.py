@@ -33,16 +33,28 @@ def main():
         # exchange variants: NVLink peer-memory pushes (default) under the host loop and inside the
         # device-side while-graph, and the NCCL send/recv path; all must give the single-GPU bits
         variants = {}
-        for vname, (p2p, loop_mode) in {"p2p_host_loop": (1, 0), "p2p_while_graph": (1, 1), "nccl": (0, 0)}.items():
+        for vname, (p2p, fuse, loop_mode) in {"p2p_fused_while_graph": (1, 1, 1), "p2p_fused_host_loop": (1, 1, 0),
+                                              "p2p_push_kernels": (1, 0, 1), "nccl": (0, 0, 0)}.items():
             sharded = gravomg.MultigridSolver(V, neigh, M, **kw)
             sharded.solver.set_option("lanes", 1)
             sharded.solver.set_option("p2p", p2p)
+            sharded.solver.set_option("p2p_fuse", fuse)
             sharded.solver.set_option("loop_mode", loop_mode)
             sharded.distribute(replicate_rows=replicate_rows)
             xs = sharded.solve(lhs, rhs)
             xs2 = sharded.solve(lhs, rhs)  # repeated solve on the staged pattern
             variants[vname] = bool(np.array_equal(x1, xs)) and bool(np.array_equal(xs, xs2)) and \
                 sharded.solver_timing["iterations"] == single.solver_timing["iterations"]
+        if name == "two_sharded_levels":
+            # the direct (non-TMA) kernels carry the same fused push / wait
+            pair = []
+            for dist_on in (False, True):
+                d = gravomg.MultigridSolver(V, neigh, M, **kw)
+                d.solver.set_option("kernel_path", 1)
+                if dist_on:
+                    d.distribute(replicate_rows=replicate_rows)
+                pair.append(d.solve(lhs, rhs))
+            variants["p2p_fused_direct_kernels"] = bool(np.array_equal(pair[0], pair[1]))
         levels = [sharded.solver.dist_ranges(k) for k in range(len(single.prolongation_matrices) + 1)]
         m = M.diagonal()
         res = float(np.sqrt(((lhs @ xs - rhs) ** 2 * m[:, None]).sum(0) / ((rhs ** 2) * m[:, None]).sum(0)).max())
