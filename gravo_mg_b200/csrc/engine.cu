@@ -60,8 +60,10 @@ struct DevMat {
         launch_expand_rows(rows, indptr.ptr, rowidx.ptr, s);
     }
     // Choose the kernel path and build the row tiles for the staged one.
+    // `early_rows` (multi-GPU, may be null): rows that are pushed to peers or gather halo entries;
+    // their tiles are moved to the front of the walk so the exchange can be signalled early.
     void make_plan(const std::vector<int>& indptr_h, int prefer_path, int staged_lanes, cudaStream_t s, int row_begin = 0,
-                   int row_end = -1) {
+                   int row_end = -1, const std::vector<char>* early_rows = nullptr) {
         if (row_end < 0) row_end = rows;
         const double avg = rows ? (double)nnz / rows : 0.0;
         int lanes = 1;
@@ -82,9 +84,17 @@ struct DevMat {
             int worst = 0;
             std::vector<int> t = plan_row_tiles(indptr_h, stage_rows, cap, &worst, row_begin, row_end);
             if (worst <= cap) {
-                std::vector<int4> desc(t.size() - 1);
-                for (size_t i = 0; i + 1 < t.size(); ++i)
-                    desc[i] = make_int4(t[i], t[i + 1], indptr_h[t[i]] & ~3, (indptr_h[t[i + 1]] + 3) & ~3);
+                std::vector<int4> desc, late;
+                desc.reserve(t.size());
+                for (size_t i = 0; i + 1 < t.size(); ++i) {
+                    const int4 d4 = make_int4(t[i], t[i + 1], indptr_h[t[i]] & ~3, (indptr_h[t[i + 1]] + 3) & ~3);
+                    bool early = false;
+                    if (early_rows)
+                        for (int r = t[i]; r < t[i + 1] && !early; ++r) early = (*early_rows)[r] != 0;
+                    (early_rows && !early ? late : desc).push_back(d4);
+                }
+                plan.n_early = early_rows ? (int)desc.size() : 0;
+                desc.insert(desc.end(), late.begin(), late.end());
                 tiles.upload(desc, s);
                 plan.path = 0;
                 plan.staged_lanes = sl;
@@ -666,6 +676,24 @@ private:
         lv_.resize(n_levels_ + 1);
         lv_[0].n = (int)st_->n;
         for (int k = 0; k < n_levels_; ++k) lv_[k + 1].n = (int)U[k].cols;
+        // multi-GPU: rows of a sharded operator that take part in an exchange, either as producer
+        // (rows peers gather, from the send lists of every halo kind whose vector has these rows) or
+        // as consumer (rows with a column outside this rank's range of the gathered vector)
+        auto early_rows = [&](const HostCsr& m, int row_level, int col_level, std::initializer_list<std::pair<int, int>> sends) {
+            std::vector<char> mark((size_t)m.rows, 0);
+            const int64_t rb = d.begin(row_level), re = d.end(row_level);
+            const bool cols_sharded = d.sharded(col_level);
+            const int64_t cb = cols_sharded ? d.begin(col_level) : 0, ce = cols_sharded ? d.end(col_level) : m.cols;
+            for (int64_t r = rb; r < re; ++r)
+                for (int q = m.indptr[r]; q < m.indptr[r + 1] && !mark[r]; ++q)
+                    if (m.indices[q] < cb || m.indices[q] >= ce) mark[r] = 1;
+            for (auto hk : sends) {
+                if (hk.second < 0 || hk.second >= (int)d.halo[hk.first].size()) continue;
+                for (const auto& list : d.halo[hk.first][hk.second].send)
+                    for (int r : list) mark[r] = 1;
+            }
+            return mark;
+        };
         int b = 0, e = -1;
         for (int k = 0; k < n_levels_; ++k) {
             const HostCsr& u = U[k];
@@ -674,12 +702,20 @@ private:
             lv_[k].P.upload_values(u.data.data(), stream_);
             lv_[k].P.refresh_cast(stream_);
             range(k, d.sharded(k), b, e);
-            lv_[k].P.make_plan(u.indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e);
+            if (d.sharded(k)) {  // prolongation: rows of level k, gathers level k + 1, writes x_k (gathered through A_k)
+                const std::vector<char> early = early_rows(u, k, k + 1, {{HALO_A, k}});
+                lv_[k].P.make_plan(u.indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e, &early);
+            } else
+                lv_[k].P.make_plan(u.indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e);
             lv_[k].R.upload_pattern(r, stream_);
             lv_[k].R.upload_values(r.data.data(), stream_);
             lv_[k].R.refresh_cast(stream_);
             range(k + 1, d.sharded(k), b, e);  // rows of R are coarse points; sharded with the fine level
-            lv_[k].R.make_plan(r.indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e);
+            if (d.sharded(k)) {  // restriction: rows of level k + 1, gathers r_k, writes b_{k+1} and the first x_{k+1}
+                const std::vector<char> early = early_rows(r, k + 1, k, {{HALO_A, k + 1}});
+                lv_[k].R.make_plan(r.indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e, &early);
+            } else
+                lv_[k].R.make_plan(r.indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e);
             lv_[k].AP.upload_pattern(st_->ap_pat[k], stream_);
             lv_[k].AP.make_rowidx(stream_);
         }
@@ -687,7 +723,11 @@ private:
             lv_[k].A.upload_pattern(st_->a_pat[k], stream_);
             if (k > 0) lv_[k].A.make_rowidx(stream_);
             range(k, d.sharded(k), b, e);
-            lv_[k].A.make_plan(st_->a_pat[k].indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e);
+            if (d.sharded(k)) {  // sweeps / residual / norm: write x_k (gathered through A_k, or U_{k-1}) or r_k (through R_k)
+                const std::vector<char> early = early_rows(st_->a_pat[k], k, k, {{HALO_A, k}, {HALO_R, k}, {HALO_P, k - 1}});
+                lv_[k].A.make_plan(st_->a_pat[k].indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e, &early);
+            } else
+                lv_[k].A.make_plan(st_->a_pat[k].indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e);
             lv_[k].dinv.ensure(std::max(lv_[k].n, 1));
         }
         // Galerkin product plans (once per pattern): which value pairs make up every entry of

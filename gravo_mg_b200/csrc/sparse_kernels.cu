@@ -328,6 +328,7 @@ int launch_one(SpmvArgs<T>& a, const SpmvPlan& plan, cudaStream_t stream) {
     if (plan.path == 0) {
         a.tile_desc = plan.tile_desc;
         a.n_tiles = plan.n_tiles;
+        a.n_early = plan.n_early;
         a.stage_elems = plan.stage_elems;
         a.stage_rows = plan.stage_rows;
         switch (plan.staged_lanes) {

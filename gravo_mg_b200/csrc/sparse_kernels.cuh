@@ -109,6 +109,8 @@ struct SpmvArgs {
     const unsigned char* send_mask = nullptr;  // [rows of out] bit q: peer q needs this row
     int push_out2 = 0;
     int wait_peers = 0;
+    int n_early = 0;                   // staged: tiles [0, n_early) hold every row that is pushed or gathers halo
+                                       // entries; the exchange is signalled once they are done (rest overlaps)
 };
 
 #ifdef __CUDACC__
@@ -124,7 +126,7 @@ __device__ __forceinline__ void peer_push_row(const SpmvArgs<T>& a, T* vec, int 
 #pragma unroll
         for (int k = 0; k < K; ++k) pv[k] = v[k];
     }
-    __threadfence_system();  // before this CTA's end-of-kernel ticket
+    // ordered before the exchange signal by the CTA barrier + system fence of peer_signal_from_cta
 }
 #endif
 
@@ -310,6 +312,11 @@ __global__ void __launch_bounds__(TPB + 32) spmv_staged_kernel(const SpmvArgs<T>
         if (a.wait_peers) peer_wait_warp(*a.fabric, const_cast<int*>(&a.ctl->error));
         const int ctid = tid - 32;
         const int lane = ctid % LANES;
+        // fused halo push: this CTA's share of the early (boundary) tiles comes first in its walk
+        const int my_early = (EPI != EPI_NORM && a.send_mask)
+                                 ? ((int)blockIdx.x < a.n_early ? (a.n_early - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0)
+                                 : -1;
+        if (my_early == 0 && ctid == 0) peer_signal_from_cta(*a.fabric, false);
         for (int it = 0; it < n_my; ++it) {
             const int s = it % STAGES;
             const unsigned char* st = stage0 + s * stage_bytes;
@@ -352,13 +359,15 @@ __global__ void __launch_bounds__(TPB + 32) spmv_staged_kernel(const SpmvArgs<T>
                 }
             }
             if (active && lane == 0) row_epilogue<T, K, EPI>(a, row, acc, ops, nrm);
+            if (it + 1 == my_early) {
+                // the boundary rows of this CTA are stored here and in the peers' HBM: count the CTA
+                // in; the last one signals the exchange while interior tiles are still being computed
+                asm volatile("bar.sync 1, %0;" ::"n"(TPB) : "memory");  // consumer warps only
+                if (ctid == 0) peer_signal_from_cta(*a.fabric, true);
+            }
         }
     }
     if (EPI == EPI_NORM || EPI == EPI_NORMJAC) block_sum_store<2 * K, TPB + 32>(nrm, a.partials + (size_t)blockIdx.x * 2 * K);
-    if (EPI != EPI_NORM && a.send_mask) {  // all rows of this CTA are stored (and fenced where pushed)
-        __syncthreads();
-        if (tid == 0) peer_signal_from_cta(*a.fabric);
-    }
 }
 
 // ---------------------------------------------------------------------------- direct path
@@ -403,9 +412,9 @@ __global__ void __launch_bounds__(kDirectThreads) spmv_direct_kernel(const SpmvA
         }
     }
     if (EPI == EPI_NORM || EPI == EPI_NORMJAC) block_sum_store<2 * K, TPB>(nrm, a.partials + (size_t)blockIdx.x * 2 * K);
-    if (EPI != EPI_NORM && a.send_mask) {
+    if (EPI != EPI_NORM && a.send_mask) {  // no tile order here: signal when the whole CTA is done
         __syncthreads();
-        if (threadIdx.x == 0) peer_signal_from_cta(*a.fabric);
+        if (threadIdx.x == 0) peer_signal_from_cta(*a.fabric, true);
     }
 }
 

@@ -11,6 +11,7 @@ struct SpmvPlan {
     int staged_lanes = 1;    // staged: threads per row (1, 2, 4, 8); 1 sums in CSR order
     int row_begin = 0, row_end = -1;  // rows this plan covers (a rank's range; -1 = all)
     int n_tiles = 0;         // staged
+    int n_early = 0;         // staged, multi-GPU: leading tiles that hold the pushed / halo-gathering rows
     int stage_elems = 0;     // staged: entries per stage (multiple of 4)
     int stage_rows = 0;      // staged: rows per tile = kStagedThreads / staged_lanes
     const int4* tile_desc = nullptr;  // device array n_tiles: {first row, end row, first entry & ~3, (end entry + 3) & ~3}
