@@ -138,62 +138,70 @@ template <bool DIAG>
 __device__ __forceinline__ void panel_factor(double (&a)[4][4], double (*Sp)[FPS], double (*Lp)[FPS],
                                              const double (*Ljj)[FS], double* rd, int tx, int ty, CycleControl* ctl) {
     const int tid = threadIdx.x;
-#pragma unroll
+    // The panel loop stays rolled: straight-line code that runs once is instruction-fetch bound
+    // (measured: the unrolled version took 2.6 us per panel, tools/factor_lab.cu).
+#pragma unroll 1
     for (int p = 0; p < FB / FP; ++p) {
         const int c0 = FP * p;
         // 1. the owners of columns c0 .. c0+7 publish their current values
         if ((ty >> 3) == (p & 1)) {
+            const int jp = p >> 1;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) Sp[tx + 16 * i][ty & 7] = a[i][p >> 1];
+            for (int i = 0; i < 4; ++i)
+                Sp[tx + 16 * i][ty & 7] = jp == 0 ? a[i][0] : jp == 1 ? a[i][1] : jp == 2 ? a[i][2] : a[i][3];
         }
         __syncthreads();
-        // 2. the 8x8 pivot block and its reciprocal diagonal, in registers, by every thread alike
+        // 2. the 8x8 pivot block and its reciprocal diagonal in registers, redundantly in every thread
+        //    that owns a row in step 3 (no broadcast); the other warps leave the fp64 pipe to them
         double d[FP][FP], rs[FP];
-        if (DIAG) {
+        if (tid < FB) {
+            if (DIAG) {
 #pragma unroll
-            for (int r = 0; r < FP; ++r)
+                for (int r = 0; r < FP; ++r)
 #pragma unroll
-                for (int k = 0; k <= r; ++k) d[r][k] = Sp[c0 + r][k];
+                    for (int k = 0; k <= r; ++k) d[r][k] = Sp[c0 + r][k];
 #pragma unroll
-            for (int k = 0; k < FP; ++k) {
-                double piv = d[k][k];
-                if (!(piv > 0.0) || piv > 1.7976931348623157e308) {
-                    if (tid == 0) atomicOr(&ctl->error, 4);
-                    piv = 1.0;
+                for (int k = 0; k < FP; ++k) {
+                    double piv = d[k][k];
+                    if (!(piv > 0.0) || piv > 1.7976931348623157e308) {
+                        if (tid == 0) atomicOr(&ctl->error, 4);
+                        piv = 1.0;
+                    }
+                    rs[k] = rsqrt(piv);
+                    d[k][k] = piv * rs[k];
+#pragma unroll
+                    for (int r = k + 1; r < FP; ++r) d[r][k] *= rs[k];
+#pragma unroll
+                    for (int j = k + 1; j < FP; ++j)
+#pragma unroll
+                        for (int r = j; r < FP; ++r) d[r][j] = fma(-d[r][k], d[j][k], d[r][j]);
                 }
-                rs[k] = rsqrt(piv);
-                d[k][k] = piv * rs[k];
+                if (tid == 0) {
 #pragma unroll
-                for (int r = k + 1; r < FP; ++r) d[r][k] *= rs[k];
+                    for (int k = 0; k < FP; ++k) rd[c0 + k] = rs[k];
+                }
+            } else {
 #pragma unroll
-                for (int j = k + 1; j < FP; ++j)
+                for (int r = 0; r < FP; ++r)
 #pragma unroll
-                    for (int r = j; r < FP; ++r) d[r][j] = fma(-d[r][k], d[j][k], d[r][j]);
+                    for (int k = 0; k <= r; ++k) d[r][k] = Ljj[c0 + r][c0 + k];
+#pragma unroll
+                for (int k = 0; k < FP; ++k) rs[k] = rd[c0 + k];
             }
-            if (tid == 0) {
-#pragma unroll
-                for (int k = 0; k < FP; ++k) rd[c0 + k] = rs[k];
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < FP; ++r)
-#pragma unroll
-                for (int k = 0; k <= r; ++k) d[r][k] = Ljj[c0 + r][c0 + k];
-#pragma unroll
-            for (int k = 0; k < FP; ++k) rs[k] = rd[c0 + k];
         }
         // 3. one thread per row: l = v D^-T (forward substitution against the pivot block)
         if (tid < FB) {
             const int row = tid;
             if (!DIAG || row >= c0 + FP) {
-                double l[FP];
+                double v[FP];
 #pragma unroll
-                for (int k = 0; k < FP; ++k) {
-                    double s = Sp[row][k];
+                for (int k = 0; k < FP; ++k) v[k] = Sp[row][k];
 #pragma unroll
-                    for (int m = 0; m < k; ++m) s = fma(-l[m], d[k][m], s);
-                    l[k] = s * rs[k];
-                    Lp[row][k] = l[k];
+                for (int k = 0; k < FP; ++k) {  // right-looking inside the row: the updates of v[k+1..] are independent
+                    const double l = v[k] * rs[k];
+                    Lp[row][k] = l;
+#pragma unroll
+                    for (int j = k + 1; j < FP; ++j) v[j] = fma(-l, d[j][k], v[j]);
                 }
             } else if (row >= c0) {
 #pragma unroll
@@ -208,7 +216,13 @@ __device__ __forceinline__ void panel_factor(double (&a)[4][4], double (*Sp)[FPS
             }
         }
         __syncthreads();
-        // 4. rank-8 update of the columns to the right; the panel's own columns become final
+        // 4. rank-8 update of the columns to the right; the panel's own columns become final.
+        //    Row operands are loaded once per panel; DIAG skips the sub-blocks above the diagonal.
+        double lr[4][FP];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < FP; ++k) lr[i][k] = Lp[tx + 16 * i][k];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int col = ty + 16 * j;
@@ -218,9 +232,10 @@ __device__ __forceinline__ void panel_factor(double (&a)[4][4], double (*Sp)[FPS
                 for (int k = 0; k < FP; ++k) cv[k] = DIAG ? Lp[col][k] : Ljj[col][c0 + k];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
+                    if (DIAG && i < j) continue;  // rows tx + 16 i < 16 j <= col: above the diagonal
                     double s = a[i][j];
 #pragma unroll
-                    for (int k = 0; k < FP; ++k) s = fma(-Lp[tx + 16 * i][k], cv[k], s);
+                    for (int k = 0; k < FP; ++k) s = fma(-lr[i][k], cv[k], s);
                     a[i][j] = s;
                 }
             } else if (col >= c0) {

@@ -984,6 +984,7 @@ private:
         const DistLayout& d = st_->dist;
         if (!d.sharded(level)) return;
         if (hop == HALO_P && !d.sharded(level + 1)) return;  // the coarse vector is replicated
+        if (st_->dist_skip_exchange) return;  // measurement only
         Op op;
         op.kind = OP_HALO, op.level = level, op.halo_op = hop, op.vec = v;
         ops_.push_back(op);
@@ -1119,7 +1120,7 @@ private:
             if (fused) op.args.dinv = lv_[0].dinv.ptr, op.args.omega_ptr = weight_ptr(0, false, 0), op.args.out = alt;
             ops_.push_back(op);
         }
-        if (use_p2p() && st_->p2p_fuse) fuse_exchanges();
+        if (use_p2p() && (st_->p2p_fuse || st_->dist_skip_exchange)) fuse_exchanges();
         cycle_dirty_ = false;
         // one-time per-kernel attribute/occupancy calls must not land inside a stream capture
         set_launch_dry_run(true);
@@ -1182,6 +1183,10 @@ private:
                 // initial guess, identical on every rank
                 for (Op& pr : prologue_)
                     if (writes(pr, v) && !mark_producer(pr, v, dh.mask.ptr)) ok = false;
+            }
+            if (st_->dist_skip_exchange) {  // measurement only: the cost of the partition without any exchange (wrong results)
+                ops_.erase(ops_.begin() + ih);
+                continue;
             }
             if (!ok) {
                 ++ih;
