@@ -91,6 +91,7 @@ SIGNATURES = {
     "gmg_kernel_profile": (C.c_int, [_h, C.c_int32, C.c_int32, _f64p, _i64p]),
     "gmg_reset_kernel_profile": (C.c_int, [_h]),
     "gmg_last_launch_count": (C.c_int, [_h, _i64p]),
+    "gmg_get_trace": (C.c_int, [_h, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _i64p]),
 }
 
 

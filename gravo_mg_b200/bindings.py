@@ -381,6 +381,16 @@ class MultigridSolver:
     def reset_kernel_profile(self):
         check(self._h, lib.gmg_reset_kernel_profile(self._h))
 
+    def trace(self):
+        """Device timeline of the last solve (option "trace"): arrays (t_ns, tag), one entry per kernel."""
+        count = C.c_int64(0)
+        check(self._h, lib.gmg_get_trace(self._h, None, None, C.byref(count)))
+        t = np.empty(count.value, dtype=np.uint64)
+        tags = np.empty(count.value, dtype=np.uint64)
+        u64 = C.POINTER(C.c_uint64)
+        check(self._h, lib.gmg_get_trace(self._h, t.ctypes.data_as(u64), tags.ctypes.data_as(u64), C.byref(count)))
+        return t, tags
+
     def last_launch_count(self):
         v = C.c_int64()
         check(self._h, lib.gmg_last_launch_count(self._h, C.byref(v)))

@@ -151,6 +151,7 @@ int gmg_set_option(gmg_handle h, const char* key, double value) {
         else if (k == "use_graph") s.use_graph = value != 0.0;
         else if (k == "loop_mode") s.loop_mode = (int)value;
         else if (k == "profile") s.profile = value != 0.0;
+        else if (k == "trace") s.trace = value != 0.0;
         else if (k == "pdl") s.use_pdl = value != 0.0, cycle = true;
         else if (k == "fuse_norm") s.fuse_norm = value != 0.0, cycle = true;
         else if (k == "tail_rows") s.tail_rows = (int)value, cycle = true;
@@ -192,6 +193,7 @@ int gmg_get_option(gmg_handle h, const char* key, double* value) {
         else if (k == "use_graph") *value = s.use_graph;
         else if (k == "loop_mode") *value = s.loop_mode;
         else if (k == "profile") *value = s.profile;
+        else if (k == "trace") *value = s.trace;
         else if (k == "pdl") *value = s.use_pdl;
         else if (k == "fuse_norm") *value = s.fuse_norm;
         else if (k == "tail_rows") *value = s.tail_rows;
@@ -504,6 +506,20 @@ int gmg_reset_kernel_profile(gmg_handle h) {
     if (!h) return 1;
     return guarded(h, [&] {
         if (h->s.engine) h->s.engine->reset_kernel_profile();
+    });
+}
+
+int gmg_get_trace(gmg_handle h, uint64_t* t_ns, uint64_t* tags, int64_t* count) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(count != nullptr, "null argument");
+        const auto& log = h->s.trace_log;
+        const int64_t n = (int64_t)log.size() / 2;
+        if (t_ns && tags) {
+            require(*count >= n, "output buffer too small");
+            for (int64_t i = 0; i < n; ++i) t_ns[i] = log[2 * i], tags[i] = log[2 * i + 1];
+        }
+        *count = n;
     });
 }
 

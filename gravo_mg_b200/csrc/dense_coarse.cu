@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(256) tri_coldot_kernel(const double* __restric
                                                          double* __restrict__ out, int out_ld, int upper,
                                                          const CycleControl* ctl) {
     if (ctl && ctl->done) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(ctl, 101 + (upper ? 0 : 1));
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (c >= n) return;

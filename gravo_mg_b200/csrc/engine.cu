@@ -274,7 +274,10 @@ public:
         GMG_CUDA(cudaEventRecord(ev_[2], stream_));
 
         // ---- "cycles" (multigrid_solver.cpp:1411-1417)
-        launch_cycle_begin(ctl_.ptr, p.max_iter, p.stopping_criteria, p.tolerance, K_, stream_);
+        constexpr int kTraceCap = 1 << 16;
+        if (st_->trace) trace_buf_.ensure(2 * (size_t)kTraceCap);
+        launch_cycle_begin(ctl_.ptr, p.max_iter, p.stopping_criteria, p.tolerance, K_, stream_,
+                           st_->trace ? trace_buf_.ptr : nullptr, st_->trace ? kTraceCap : 0);
         ++launches;
         for (const Op& op : prologue_) launches += run_op(op, stream_, 0);
         // multi-GPU: the NCCL exchanges are captured into the cycle graph too (option dist_graph)
@@ -298,6 +301,12 @@ public:
         GMG_CUDA(cudaMemcpyAsync(ctl_host_, ctl_.ptr, sizeof(CycleControl), cudaMemcpyDeviceToHost, stream_));
         GMG_CUDA(cudaStreamSynchronize(stream_));
         if (st_->profile) collect_profile();
+        st_->trace_log.clear();
+        if (st_->trace) {
+            const int nt = std::min(ctl_host_->trace_n, ctl_host_->trace_cap);
+            st_->trace_log.resize(2 * (size_t)nt);
+            if (nt) GMG_CUDA(cudaMemcpy(st_->trace_log.data(), trace_buf_.ptr, 2 * (size_t)nt * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        }
 
         const int iters = ctl_host_->iter;
         launches += (int64_t)iters * launches_per_cycle_;
@@ -1480,6 +1489,7 @@ private:
     CycleControl* ctl_host_ = nullptr;
     DeviceBuffer<double> hist_res_, hist_ms_, partials_, mass_, minv_, rhs64_, x64_, coarse_b64_, coarse_x64_, io64_;
     DeviceBuffer<double> rho_, weights64_;
+    DeviceBuffer<unsigned long long> trace_buf_;
     DeviceBuffer<T> weights_;
     DeviceBuffer<int> q_indptr_, q_indices_;
     DeviceBuffer<double> q_vals_, q_b_, q_x_;

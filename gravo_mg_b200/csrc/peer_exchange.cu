@@ -46,6 +46,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) peer_push_kernel(const PeerPushArgs<T> a, const PeerFabric f, CycleControl* ctl) {
     grid_dependency_wait();    // the kernel that wrote v must be complete
     grid_launch_dependents();  // the consumer may prefetch its operator slabs; it waits for this grid before it gathers
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(ctl, 103);
     const int K = a.K;
     for (int q = 0; q < f.world; ++q) {
         const int cnt = a.count[q];
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(256) peer_norm_kernel(const double* __restrict
                                                         double* hist_ms, unsigned long long cond_handle) {
     grid_dependency_wait();
     grid_launch_dependents();
+    if (threadIdx.x == 0) trace_mark(ctl, 104);
     __shared__ double sums[kPeerNormSlots];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int n_sums = 0;

@@ -47,6 +47,8 @@ struct SolverState {
     int kernel_path = 0;             // 0 staged (TMA) where it fits, 1 direct everywhere
     int staged_lanes = 0;            // staged kernels: threads per row; 0 = from the mean row length
     bool profile = false;
+    bool trace = false;              // device timeline: (globaltimer, tag) per kernel of the cycles (gmg_get_trace)
+    std::vector<unsigned long long> trace_log;
     int tail_rows = 0;               // levels with at most this many rows run inside the fused tail kernel; off by
                                      // default: measured slower than PDL-chained kernels ("Coarse tail")
     bool dist_graph = true;          // multi-GPU: capture the cycle (kernels + NCCL exchanges) into a CUDA graph

@@ -8,7 +8,11 @@
 namespace gmg {
 
 // ------------------------------------------------------------------ small device kernels
-__global__ void cycle_begin_kernel(CycleControl* ctl, int max_iter, int criterion, double tol, int n_cols) {
+__global__ void cycle_begin_kernel(CycleControl* ctl, int max_iter, int criterion, double tol, int n_cols,
+                                   unsigned long long* trace, int trace_cap) {
+    ctl->trace = trace;
+    ctl->trace_n = 0;
+    ctl->trace_cap = trace_cap;
     ctl->iter = 0;
     ctl->done = 0;
     ctl->max_iter = max_iter;
@@ -26,6 +30,7 @@ __global__ void norm_finalize_kernel(const double* __restrict__ partials, NormCh
         if (cond_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, 0);
         return;
     }
+    if (threadIdx.x == 0) trace_mark(ctl, 100);
     __shared__ double sums[2 * kMaxRhsTile * kMaxNormChunks];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int n_sums = 0;
@@ -421,8 +426,9 @@ template void launch_pack<float>(const float*, const int*, int, int, float*, cud
 template void launch_unpack<double>(double*, const int*, int, int, const double*, cudaStream_t);
 template void launch_unpack<float>(float*, const int*, int, int, const float*, cudaStream_t);
 
-void launch_cycle_begin(CycleControl* ctl, int max_iter, int criterion, double tol, int n_cols, cudaStream_t stream) {
-    cycle_begin_kernel<<<1, 1, 0, stream>>>(ctl, max_iter, criterion, tol, n_cols);
+void launch_cycle_begin(CycleControl* ctl, int max_iter, int criterion, double tol, int n_cols, cudaStream_t stream,
+                        unsigned long long* trace, int trace_cap) {
+    cycle_begin_kernel<<<1, 1, 0, stream>>>(ctl, max_iter, criterion, tol, n_cols, trace, trace_cap);
     GMG_CUDA(cudaGetLastError());
 }
 

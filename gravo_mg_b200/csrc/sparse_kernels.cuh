@@ -40,11 +40,22 @@ struct CycleControl {
     double tol;
     double residue;
     unsigned long long t_start_ns;
-    int error;      // sticky: 1 bad diagonal, 2 non-finite residual, 4 coarse factor breakdown
+    int error;      // sticky: 1 bad diagonal, 2 non-finite residual, 4 coarse factor breakdown, 8 peer timeout, 16 factor stall
     int n_cols;
+    // optional device timeline (option "trace"): one (globaltimer ns, tag) pair per kernel of the cycle
+    unsigned long long* trace;
+    int trace_n, trace_cap;
 };
 
 #ifdef __CUDACC__
+// One thread per kernel: the time at which the kernel's dependencies were met, and what it is.
+__device__ __forceinline__ void trace_mark(const CycleControl* ctl, unsigned long long tag) {
+    if (ctl == nullptr || ctl->trace == nullptr) return;
+    CycleControl* c = const_cast<CycleControl*>(ctl);
+    const int i = atomicAdd(&c->trace_n, 1);
+    if (i < c->trace_cap) c->trace[2 * i] = global_timer_ns(), c->trace[2 * i + 1] = tag;
+}
+
 // Stopping rule of the cycle loop (multigrid_solver.cpp:1228-1277 norms, :1413-1417 loop test) from
 // the 2K sums {sum w r^2, sum w b^2} per right-hand side; one thread. record = 0: only the residue.
 __device__ inline void apply_stopping_rule(const double* sums, int K, CycleControl* ctl, double* hist_res, double* hist_ms,
@@ -312,6 +323,7 @@ __global__ void __launch_bounds__(TPB + 32) spmv_staged_kernel(const SpmvArgs<T>
         if (a.wait_peers) peer_wait_warp(*a.fabric, const_cast<int*>(&a.ctl->error));
         const int ctid = tid - 32;
         const int lane = ctid % LANES;
+        if (blockIdx.x == 0 && ctid == 0) trace_mark(a.ctl, ((unsigned long long)a.n_rows << 8) | (unsigned)EPI);
         // fused halo push: this CTA's share of the early (boundary) tiles comes first in its walk
         const int my_early = (EPI != EPI_NORM && a.send_mask)
                                  ? ((int)blockIdx.x < a.n_early ? (a.n_early - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0)
@@ -377,6 +389,7 @@ __global__ void __launch_bounds__(kDirectThreads) spmv_direct_kernel(const SpmvA
     grid_dependency_wait();
     grid_launch_dependents();
     if (a.wait_peers) peer_wait_warp(*a.fabric, const_cast<int*>(&a.ctl->error));
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(a.ctl, ((unsigned long long)a.n_rows << 8) | (unsigned)EPI);
     const int lane = threadIdx.x % LANES;
     const int rows_per_block = TPB / LANES;
     double nrm[2 * K];

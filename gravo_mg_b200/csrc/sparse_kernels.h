@@ -56,7 +56,8 @@ template <typename T>
 void launch_pack(const T* v, const int* idx, int n, int K, T* buf, cudaStream_t stream);
 template <typename T>
 void launch_unpack(T* v, const int* idx, int n, int K, const T* buf, cudaStream_t stream);
-void launch_cycle_begin(CycleControl* ctl, int max_iter, int criterion, double tol, int n_cols, cudaStream_t stream);
+void launch_cycle_begin(CycleControl* ctl, int max_iter, int criterion, double tol, int n_cols, cudaStream_t stream,
+                        unsigned long long* trace = nullptr, int trace_cap = 0);
 
 constexpr int kMaxSweeps = 16;        // pre / post sweeps per level the weight table holds
 

@@ -186,6 +186,11 @@ int gmg_time_op(gmg_handle h, int32_t kind, int32_t level, int32_t reps, double*
 int gmg_kernel_profile(gmg_handle h, int32_t kind, int32_t level, double* total_ms, int64_t* launches);
 int gmg_reset_kernel_profile(gmg_handle h);
 /* Number of kernel launches issued (or replayed through graphs) by the last solve. */
+/* Device timeline of the last solve (option "trace" = 1): for every kernel of the cycles the
+ * globaltimer value at which its dependencies were met, and a tag (rows << 8 | epilogue for the
+ * row-product kernels; 100 stopping test, 101 / 102 coarse solve, 103 / 104 multi-GPU push / norm).
+ * Query the count with t_ns == NULL. Measurement aid, no reference counterpart. */
+int gmg_get_trace(gmg_handle h, uint64_t* t_ns, uint64_t* tags, int64_t* count);
 int gmg_last_launch_count(gmg_handle h, int64_t* launches);
 
 #ifdef __cplusplus
