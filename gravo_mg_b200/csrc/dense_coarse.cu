@@ -269,12 +269,16 @@ __global__ void transpose_kernel(const double* __restrict__ src, double* __restr
 }
 
 // out_c = sum over the stored triangle of column c of M: rows [0, c] (upper) or [c, n) (lower).
-// One warp per column, rows read contiguously; the fixed lane/shuffle order keeps it deterministic.
+// One warp per column, rows read contiguously, eight independent 32-row strips in flight per lane
+// (the loop is latency bound: a column is at most n / 32 strips long); the fixed strip / shuffle
+// order keeps it deterministic. Launched with programmatic dependent launch like the row products.
 template <int K>
 __global__ void __launch_bounds__(256) tri_coldot_kernel(const double* __restrict__ M, int ld, int n,
                                                          const double* __restrict__ v, int v_ld,
                                                          double* __restrict__ out, int out_ld, int upper,
                                                          const CycleControl* ctl) {
+    grid_dependency_wait();
+    grid_launch_dependents();
     if (ctl && ctl->done) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(ctl, 101 + (upper ? 0 : 1));
     const int lane = threadIdx.x & 31;
@@ -285,10 +289,21 @@ __global__ void __launch_bounds__(256) tri_coldot_kernel(const double* __restric
     double acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.0;
-    for (int r = lo + lane; r < hi; r += 32) {
-        const double m = col[r];
+    constexpr int U = 8;
+    for (int r0 = lo + lane; r0 < hi; r0 += 32 * U) {
+        double m[U], w[U][K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = fma(m, v[(size_t)r * v_ld + k], acc[k]);
+        for (int u = 0; u < U; ++u) {
+            const int r = r0 + 32 * u;
+            const bool in = r < hi;
+            m[u] = in ? col[r] : 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) w[u][k] = in ? v[(size_t)r * v_ld + k] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = fma(m[u], w[u][k], acc[k]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
@@ -302,8 +317,16 @@ __global__ void __launch_bounds__(256) tri_coldot_kernel(const double* __restric
 template <int K>
 void launch_coldot(const double* M, int ld, int n, const double* v, int v_ld, double* out, int out_ld, int upper,
                    const CycleControl* ctl, cudaStream_t s) {
-    tri_coldot_kernel<K><<<(n + 7) / 8, 256, 0, s>>>(M, ld, n, v, v_ld, out, out_ld, upper, ctl);
-    GMG_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((n + 7) / 8), 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GMG_CUDA(cudaLaunchKernelEx(&cfg, tri_coldot_kernel<K>, M, ld, n, v, v_ld, out, out_ld, upper, ctl));
 }
 
 void coldot(int K, const double* M, int ld, int n, const double* v, int v_ld, double* out, int out_ld, int upper,
