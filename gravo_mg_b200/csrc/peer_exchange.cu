@@ -3,42 +3,17 @@
 namespace gmg {
 namespace {
 
-// All blocks of the calling kernel have stored their data into peer memory. The last block to get
-// here publishes this rank's next epoch to every peer and waits until every peer has published
-// the same epoch (i.e. its stores into OUR arena are complete and visible).
+// All threads of the calling kernel have stored their data into peer memory. One thread per block
+// counts the block in (peer_signal_from_cta: the last block publishes this rank's next epoch with
+// a single system-scope fence); the last block then waits until every peer has published the same
+// epoch, i.e. the peers' stores into OUR arena are complete and visible.
 __device__ void peer_handshake(const PeerFabric& f, CycleControl* ctl) {
-    __shared__ unsigned long long sh_epoch;
     __shared__ int sh_last;
-    __threadfence_system();  // this thread's peer stores before the ticket
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned t = atomicAdd(f.ticket, 1u);
-        __threadfence_system();  // acquire side: the other blocks' stores happen before our flag store
-        sh_last = (t == gridDim.x - 1);
-    }
+    if (threadIdx.x == 0) sh_last = peer_signal_from_cta(f, true) ? 1 : 0;
     __syncthreads();
     if (!sh_last) return;
-    if (threadIdx.x == 0) {
-        *f.ticket = 0;
-        const unsigned long long e = *f.epoch + 1;
-        *f.epoch = e;
-        sh_epoch = e;
-    }
-    __syncthreads();
-    const unsigned long long e = sh_epoch;
-    const int q = threadIdx.x;
-    if (q < f.world && q != f.rank) {
-        __threadfence_system();
-        st_release_sys(&on_peer(f.box, f, q)->flags[f.rank], e);
-        const unsigned long long t0 = global_timer_ns();
-        // after one timeout the solve is lost: keep signalling (peers may still be alive) but stop waiting
-        while (!(*const_cast<volatile int*>(&ctl->error) & 8) && ld_acquire_sys(&f.box->flags[q]) < e) {
-            if (global_timer_ns() - t0 > kPeerTimeoutNs) {
-                atomicOr(&ctl->error, 8);
-                break;
-            }
-        }
-    }
+    peer_wait_warp(f, &ctl->error);  // every warp of the last block (cheap), so all its threads may read peer data after
     __syncthreads();
 }
 
@@ -131,7 +106,7 @@ void launch_peer_push(const PeerPushArgs<T>& args, const PeerFabric& fabric, Cyc
     long long most = 0;
     for (int q = 0; q < fabric.world; ++q)
         if (q != fabric.rank) most = std::max(most, (long long)args.count[q] * args.K);
-    const int grid = (int)std::min<long long>(std::max<long long>((most + 255) / 256, 1), 4 * 148);
+    const int grid = (int)std::min<long long>(std::max<long long>((most + 1023) / 1024, 1), 148);
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
     launch_cfg(cfg, attr, grid, stream);

@@ -38,20 +38,30 @@ __device__ __forceinline__ P* on_peer(P* local, const PeerFabric& f, int q) {
     return reinterpret_cast<P*>(reinterpret_cast<char*>(local) + f.peer_delta[q]);
 }
 
-// Producer side of a fused exchange, called by ONE thread of every CTA of the grid exactly once,
-// after the CTA's threads have stored the rows peers need and met at a barrier. `pushed`: this CTA
-// stored into peer memory (needs the system-scope fence, 2.6 us on B200; a CTA that only counts
-// itself in does not). The last CTA of the grid advances this rank's epoch and publishes it.
-__device__ __forceinline__ void peer_signal_from_cta(const PeerFabric& f, bool pushed) {
-    if (pushed) __threadfence_system();
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Producer side of an exchange, called by ONE thread of every CTA of the grid exactly once, after
+// the CTA's threads have stored the rows peers need and met at a barrier. `pushed`: this CTA
+// stored into peer memory. The last CTA of the grid advances this rank's epoch and publishes it.
+//
+// Memory order (PTX model): a pushing CTA releases its stores at gpu scope (fence + ticket
+// increment); the last CTA acquires all tickets and then releases at SYSTEM scope (one fence.sys,
+// measured 2.6 us on B200, then the flag stores). Release is cumulative, so the peer that acquires
+// the flag also sees the other CTAs' rows. Only the last CTA pays the system fence.
+// Returns true in the CTA that published.
+__device__ __forceinline__ bool peer_signal_from_cta(const PeerFabric& f, bool pushed) {
+    if (pushed) __threadfence();
     const unsigned t = atomicAdd(f.ticket, 1u);
-    if (t != gridDim.x - 1) return;
-    __threadfence();  // the other CTAs' (fenced) peer stores happen before our flag stores
+    if (t != gridDim.x - 1) return false;
+    __threadfence_system();
     *f.ticket = 0;
     const unsigned long long e = *f.epoch + 1;
     *f.epoch = e;
     for (int q = 0; q < f.world; ++q)
-        if (q != f.rank) st_release_sys(&on_peer(f.box, f, q)->flags[f.rank], e);
+        if (q != f.rank) st_relaxed_sys(&on_peer(f.box, f, q)->flags[f.rank], e);
+    return true;
 }
 
 // Consumer side, called by a full warp: returns when every peer has signalled this rank's
