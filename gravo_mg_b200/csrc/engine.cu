@@ -32,6 +32,10 @@ struct DevMat {
     DeviceBuffer<long long> pair_off;   // product plan of the Galerkin step that fills this matrix
     DeviceBuffer<int2> pairs;           //   (sparse_kernels.h, build_spgemm_plan); empty: search per solve
     bool planned = false;
+    // multi-GPU: the stored entries this rank computes in the Galerkin product ([e0, e1); all by default)
+    // and, for the level operators, every rank's share (entry offsets, world + 1) for the all-gather
+    int64_t e0 = 0, e1 = -1;
+    std::vector<int64_t> share;
     DeviceBuffer<int4> tiles;
     DeviceBuffer<double> v64;
     DeviceBuffer<float> v32;
@@ -394,16 +398,27 @@ public:
         for (int k = 0; k < L; ++k) {
             Level& f = lv_[k];
             Level& c = lv_[k + 1];
+            const int64_t na = f.AP.e1 - f.AP.e0, nc = c.A.e1 - c.A.e0;
             if (f.AP.planned)
-                launch_spgemm_planned(f.AP.nnz, f.AP.pair_off.ptr, f.AP.pairs.ptr, f.A.v64.ptr, f.P.v64.ptr, f.AP.v64.ptr, stream_);
+                launch_spgemm_planned(na, f.AP.pair_off.ptr, f.AP.pairs.ptr, f.A.v64.ptr, f.P.v64.ptr, f.AP.v64.ptr + f.AP.e0, stream_);
             else
-                launch_spgemm_numeric(f.AP.nnz, f.AP.rowidx.ptr, f.AP.indices.ptr, f.AP.v64.ptr, f.A.indptr.ptr, f.A.indices.ptr,
-                                      f.A.v64.ptr, f.P.indptr.ptr, f.P.indices.ptr, f.P.v64.ptr, stream_);
+                launch_spgemm_numeric(na, f.AP.rowidx.ptr + f.AP.e0, f.AP.indices.ptr + f.AP.e0, f.AP.v64.ptr + f.AP.e0, f.A.indptr.ptr,
+                                      f.A.indices.ptr, f.A.v64.ptr, f.P.indptr.ptr, f.P.indices.ptr, f.P.v64.ptr, stream_);
             if (c.A.planned)
-                launch_spgemm_planned(c.A.nnz, c.A.pair_off.ptr, c.A.pairs.ptr, f.R.v64.ptr, f.AP.v64.ptr, c.A.v64.ptr, stream_);
+                launch_spgemm_planned(nc, c.A.pair_off.ptr, c.A.pairs.ptr, f.R.v64.ptr, f.AP.v64.ptr, c.A.v64.ptr + c.A.e0, stream_);
             else
-                launch_spgemm_numeric(c.A.nnz, c.A.rowidx.ptr, c.A.indices.ptr, c.A.v64.ptr, f.R.indptr.ptr, f.R.indices.ptr,
-                                      f.R.v64.ptr, f.AP.indptr.ptr, f.AP.indices.ptr, f.AP.v64.ptr, stream_);
+                launch_spgemm_numeric(nc, c.A.rowidx.ptr + c.A.e0, c.A.indices.ptr + c.A.e0, c.A.v64.ptr + c.A.e0, f.R.indptr.ptr,
+                                      f.R.indices.ptr, f.R.v64.ptr, f.AP.indptr.ptr, f.AP.indices.ptr, f.AP.v64.ptr, stream_);
+            if (!c.A.share.empty()) {
+                // every rank computed the rows of its coarse range: all-gather the values of A_{k+1}
+                GMG_NCCL(nccl().GroupStart());
+                for (int q = 0; q < st_->dist.world; ++q) {
+                    const size_t cnt = (size_t)(c.A.share[q + 1] - c.A.share[q]);
+                    double* at = c.A.v64.ptr + c.A.share[q];
+                    if (cnt) GMG_NCCL(nccl().Broadcast(at, at, cnt, ncclDouble, q, comm_, stream_));
+                }
+                GMG_NCCL(nccl().GroupEnd());
+            }
             launches += 2;
             if (k + 1 < L) {
                 launch_extract_dinv<T>(c.n, c.A.indptr.ptr, c.A.indices.ptr, c.A.v64.ptr, c.dinv.ptr, rho_.ptr + k + 1, ctl_.ptr,
@@ -746,12 +761,33 @@ private:
             Level& f = lv_[k];
             Level& c = lv_[k + 1];
             f.AP.planned = c.A.planned = false;
+            // multi-GPU: a sharded fine level computes only its share of the product — the rows of
+            // A_{k+1} in this rank's coarse range and the rows of A_k U_k those need (own fine range plus
+            // the rows its restriction gathers); the level operator is all-gathered per solve
+            f.AP.e0 = 0, f.AP.e1 = f.AP.nnz, c.A.e0 = 0, c.A.e1 = c.A.nnz, c.A.share.clear();
+            if (d.sharded(k) && st_->dist_shard_setup) {
+                const HostCsr& r = st_->r_host[k];
+                const HostCsr& ap = st_->ap_pat[k];
+                const HostCsr& ac = st_->a_pat[k + 1];
+                const int64_t cb = d.begin(k + 1), ce = d.end(k + 1);
+                int64_t lo = d.begin(k), hi = d.end(k);
+                for (int64_t I = cb; I < ce; ++I)
+                    for (int q = r.indptr[I]; q < r.indptr[I + 1]; ++q) {
+                        lo = std::min<int64_t>(lo, r.indices[q]);
+                        hi = std::max<int64_t>(hi, (int64_t)r.indices[q] + 1);
+                    }
+                if (ce <= cb) lo = hi = d.begin(k);
+                f.AP.e0 = ap.indptr[lo], f.AP.e1 = ap.indptr[hi];
+                c.A.e0 = ac.indptr[cb], c.A.e1 = ac.indptr[ce];
+                c.A.share.resize(d.world + 1);
+                for (int q = 0; q <= d.world; ++q) c.A.share[q] = ac.indptr[d.ranges[k + 1][q]];
+            }
             if (!st_->spgemm_plan || plan_pairs > st_->spgemm_plan_max_pairs) continue;
-            plan_pairs += build_spgemm_plan(f.AP.nnz, f.AP.rowidx.ptr, f.AP.indices.ptr, f.A.indptr.ptr, f.A.indices.ptr,
-                                            f.P.indptr.ptr, f.P.indices.ptr, f.AP.pair_off, f.AP.pairs, stream_);
+            plan_pairs += build_spgemm_plan(f.AP.e1 - f.AP.e0, f.AP.rowidx.ptr + f.AP.e0, f.AP.indices.ptr + f.AP.e0, f.A.indptr.ptr,
+                                            f.A.indices.ptr, f.P.indptr.ptr, f.P.indices.ptr, f.AP.pair_off, f.AP.pairs, stream_);
             f.AP.planned = true;
-            plan_pairs += build_spgemm_plan(c.A.nnz, c.A.rowidx.ptr, c.A.indices.ptr, f.R.indptr.ptr, f.R.indices.ptr,
-                                            f.AP.indptr.ptr, f.AP.indices.ptr, c.A.pair_off, c.A.pairs, stream_);
+            plan_pairs += build_spgemm_plan(c.A.e1 - c.A.e0, c.A.rowidx.ptr + c.A.e0, c.A.indices.ptr + c.A.e0, f.R.indptr.ptr,
+                                            f.R.indices.ptr, f.AP.indptr.ptr, f.AP.indices.ptr, c.A.pair_off, c.A.pairs, stream_);
             c.A.planned = true;
         }
         st_->transfer_timing["galerkin_plan_pairs"] = (double)plan_pairs;

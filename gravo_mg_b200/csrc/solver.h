@@ -54,6 +54,7 @@ struct SolverState {
     bool dist_graph = true;          // multi-GPU: capture the cycle (kernels + NCCL exchanges) into a CUDA graph
     bool p2p = true;                 // multi-GPU: halos and norms through NVLink peer memory (peer_exchange.h);
                                      // false: pack / ncclSend / ncclRecv / unpack and ncclAllReduce
+    bool dist_shard_setup = true;    // multi-GPU: sharded levels compute their share of the Galerkin product, values all-gathered
     bool dist_skip_exchange = false; // measurement only: drop the halo exchanges of the cycle (results are wrong)
     bool p2p_fuse = true;            // p2p: pushes fused into the producing kernels, waits into the consuming ones
     bool fuse_norm = true;           // stopping test fused with the next cycle's first sweep

@@ -33,13 +33,15 @@ def main():
         # exchange variants: NVLink peer-memory pushes (default) under the host loop and inside the
         # device-side while-graph, and the NCCL send/recv path; all must give the single-GPU bits
         variants = {}
-        for vname, (p2p, fuse, loop_mode) in {"p2p_fused_while_graph": (1, 1, 1), "p2p_fused_host_loop": (1, 1, 0),
-                                              "p2p_push_kernels": (1, 0, 1), "nccl": (0, 0, 0)}.items():
+        for vname, (p2p, fuse, loop_mode, shard_setup) in {"p2p_fused_while_graph": (1, 1, 1, 1), "p2p_fused_host_loop": (1, 1, 0, 1),
+                                                           "p2p_push_kernels": (1, 0, 1, 1), "nccl": (0, 0, 0, 1),
+                                                           "replicated_galerkin_setup": (1, 1, 1, 0)}.items():
             sharded = gravomg.MultigridSolver(V, neigh, M, **kw)
             sharded.solver.set_option("lanes", 1)
             sharded.solver.set_option("p2p", p2p)
             sharded.solver.set_option("p2p_fuse", fuse)
             sharded.solver.set_option("loop_mode", loop_mode)
+            sharded.solver.set_option("dist_shard_setup", shard_setup)
             sharded.distribute(replicate_rows=replicate_rows)
             xs = sharded.solve(lhs, rhs)
             xs2 = sharded.solve(lhs, rhs)  # repeated solve on the staged pattern
