@@ -160,7 +160,7 @@ int gmg_set_option(gmg_handle h, const char* key, double value) {
         else if (k == "xfer_threads") s.xfer_threads = (int)value;
         else if (k == "p2p") s.p2p = value != 0.0, hierarchy = true;
         else if (k == "p2p_fuse") s.p2p_fuse = value != 0.0, cycle = true;
-        else if (k == "dist_shard_setup") s.dist_shard_setup = value != 0.0, hierarchy = true;
+        else if (k == "dist_shard_setup") s.dist_shard_setup = (int)value, hierarchy = true;
         else if (k == "dist_skip_exchange") s.dist_skip_exchange = value != 0.0, cycle = true;
         else if (k == "spgemm_plan") s.spgemm_plan = value != 0.0, hierarchy = true;
         else if (k == "coarse_dataflow") s.coarse_dataflow = value != 0.0, cycle = true;

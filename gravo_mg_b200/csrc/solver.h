@@ -54,7 +54,9 @@ struct SolverState {
     bool dist_graph = true;          // multi-GPU: capture the cycle (kernels + NCCL exchanges) into a CUDA graph
     bool p2p = true;                 // multi-GPU: halos and norms through NVLink peer memory (peer_exchange.h);
                                      // false: pack / ncclSend / ncclRecv / unpack and ncclAllReduce
-    bool dist_shard_setup = true;    // multi-GPU: sharded levels compute their share of the Galerkin product, values all-gathered
+    int dist_shard_setup = -1;       // multi-GPU: sharded levels compute only their share of the Galerkin product and the
+                                     // values are all-gathered (NCCL). -1: from 4 ranks on (measured: at 2 ranks the two
+                                     // all-gathers cost more than the halved products save), 0 replicated, 1 sharded
     bool dist_skip_exchange = false; // measurement only: drop the halo exchanges of the cycle (results are wrong)
     bool p2p_fuse = true;            // p2p: pushes fused into the producing kernels, waits into the consuming ones
     bool fuse_norm = true;           // stopping test fused with the next cycle's first sweep
