@@ -102,7 +102,7 @@ class MultigridSolver:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and lib is not None:  # `lib` is already None when the interpreter tears the module down
             lib.gmg_destroy(h)
             self._h = None
 

@@ -1378,6 +1378,12 @@ private:
                 NormChunks chunks;
                 SpmvArgs<T> a = op.args;
                 a.weight = p.stopping_criteria == 2 ? mass_.ptr : p.stopping_criteria == 1 ? minv_.ptr : nullptr;
+                // single GPU, one column pass: the kernel's last CTA is the stopping test
+                const bool fused_test = st_->dist.world <= 1 && K_ <= kMaxRhsTile && st_->fuse_stop;
+                if (fused_test) {
+                    a.fin_ticket = tail_bar_.ptr + 2;
+                    a.hist_res = hist_res_.ptr, a.hist_ms = hist_ms_.ptr, a.cond_handle = cond;
+                }
                 for (int k0 = 0; k0 < K_; k0 += kMaxRhsTile) {
                     const int kt = std::min(kMaxRhsTile, K_ - k0);
                     a.x = op.args.x + k0, a.b = op.args.b + k0;
@@ -1388,6 +1394,7 @@ private:
                     ++chunks.n_chunks;
                     ++launches;
                 }
+                if (fused_test) break;
                 if (use_p2p()) {
                     // rows are split across ranks: partial sums travel through the peers' mailboxes
                     launch_peer_norm(partials_.ptr, chunks, K_, fabric_, ctl_.ptr, hist_res_.ptr, hist_ms_.ptr, cond, s);

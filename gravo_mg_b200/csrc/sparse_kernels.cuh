@@ -120,6 +120,12 @@ struct SpmvArgs {
     const unsigned char* send_mask = nullptr;  // [rows of out] bit q: peer q needs this row
     int push_out2 = 0;
     int wait_peers = 0;
+    // stopping test fused into the NORM / NORMJAC kernel (single GPU, K <= 4): the last CTA reduces the
+    // per-CTA partial sums and applies the stopping rule (what norm_finalize_kernel does otherwise)
+    unsigned* fin_ticket = nullptr;
+    double* hist_res = nullptr;
+    double* hist_ms = nullptr;
+    unsigned long long cond_handle = 0;
     int n_early = 0;                   // staged: tiles [0, n_early) hold every row that is pushed or gathers halo
                                        // entries; the exchange is signalled once they are done (rest overlaps)
 };
@@ -161,6 +167,35 @@ __device__ __forceinline__ void block_sum_store(double (&v)[NV], double* out) {
         double s = 0.0;
         for (int w = 0; w < TPB / 32; ++w) s += sh[threadIdx.x][w];
         out[threadIdx.x] = s;
+    }
+}
+
+// NORM kernels with a.fin_ticket: the last CTA of the grid adds the per-CTA partial sums (lane-strided
+// over the CTAs, then a shuffle butterfly: the order norm_finalize_kernel uses) and applies the stopping rule.
+template <int K>
+__device__ __forceinline__ void fused_stopping_test(const double* partials, unsigned* ticket, CycleControl* ctl,
+                                                    double* hist_res, double* hist_ms, unsigned long long cond_handle) {
+    __shared__ int sh_last;
+    __shared__ double sh_sums[2 * K];
+    __threadfence();  // this CTA's partial sums before its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) sh_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!sh_last) return;
+    __threadfence();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (int j = warp; j < 2 * K; j += n_warps) {
+        double s = 0.0;
+        for (int blk = lane; blk < (int)gridDim.x; blk += 32) s += __ldcg(partials + (size_t)blk * 2 * K + j);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) sh_sums[j] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *ticket = 0;
+        trace_mark(ctl, 100);
+        apply_stopping_rule(sh_sums, K, ctl, hist_res, hist_ms, 1, cond_handle);
     }
 }
 
@@ -379,7 +414,11 @@ __global__ void __launch_bounds__(TPB + 32) spmv_staged_kernel(const SpmvArgs<T>
             }
         }
     }
-    if (EPI == EPI_NORM || EPI == EPI_NORMJAC) block_sum_store<2 * K, TPB + 32>(nrm, a.partials + (size_t)blockIdx.x * 2 * K);
+    if (EPI == EPI_NORM || EPI == EPI_NORMJAC) {
+        block_sum_store<2 * K, TPB + 32>(nrm, a.partials + (size_t)blockIdx.x * 2 * K);
+        if (a.fin_ticket)
+            fused_stopping_test<K>(a.partials, a.fin_ticket, const_cast<CycleControl*>(a.ctl), a.hist_res, a.hist_ms, a.cond_handle);
+    }
 }
 
 // ---------------------------------------------------------------------------- direct path
@@ -424,7 +463,11 @@ __global__ void __launch_bounds__(kDirectThreads) spmv_direct_kernel(const SpmvA
             row_epilogue<T, K, EPI>(a, row, acc, ops, nrm);
         }
     }
-    if (EPI == EPI_NORM || EPI == EPI_NORMJAC) block_sum_store<2 * K, TPB>(nrm, a.partials + (size_t)blockIdx.x * 2 * K);
+    if (EPI == EPI_NORM || EPI == EPI_NORMJAC) {
+        block_sum_store<2 * K, TPB>(nrm, a.partials + (size_t)blockIdx.x * 2 * K);
+        if (a.fin_ticket)
+            fused_stopping_test<K>(a.partials, a.fin_ticket, const_cast<CycleControl*>(a.ctl), a.hist_res, a.hist_ms, a.cond_handle);
+    }
     if (EPI != EPI_NORM && a.send_mask) {  // no tile order here: signal when the whole CTA is done
         __syncthreads();
         if (threadIdx.x == 0) peer_signal_from_cta(*a.fabric, true);

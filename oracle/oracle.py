@@ -204,7 +204,7 @@ class OracleSolver:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and lib is not None:  # module globals are gone when the interpreter shuts down
             lib().orc_destroy(h)
             self._h = None
 

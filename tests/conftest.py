@@ -94,3 +94,30 @@ def torus_mid():
     from gravo_mg_b200 import synth
 
     return Problem(*synth.torus_grid(300, 300), kind="poisson")
+
+
+class CloudProblem(Problem):
+    """BASELINE config 4 in small: jittered point cloud on a torus, symmetrised k = 8 nearest-neighbour
+    graph Laplacian as stiffness, M = I / N, Poisson system (no faces: neighbours come from the graph)."""
+
+    def __init__(self, n_side, lower_bound=500, **solver_kw):
+        import gravomg
+        from gravo_mg_b200 import synth
+
+        P = synth.torus_cloud(n_side, seed=0)
+        nbr = synth.knn_grid(P, n_side, k=8)
+        self.S, self.M = synth.knn_graph_laplacian(nbr)
+        self.V = P.reshape(-1, 3) if P.ndim == 3 else P
+        self.F = None
+        self.neigh = gravomg.util.neighbors_from_stiffness(self.S)
+        self.m = self.M.diagonal()
+        self.lhs, self.rhs = synth.poisson_system(self.S, self.M)
+        self.solver_kw = dict(lower_bound=lower_bound, **solver_kw)
+        self.solver = gravomg.MultigridSolver(self.V, self.neigh, self.M, **self.solver_kw)
+        self.U = self.solver.prolongation_matrices
+
+
+@pytest.fixture(scope="session")
+def cloud_mid():
+    """40 000-point kNN cloud (200 x 200 jittered torus samples), Poisson."""
+    return CloudProblem(200)

@@ -281,7 +281,7 @@ def test_p2_one_vcycle_poisson(ico_small):
 
 
 # ------------------------------------------------------------------------------ P3: whole solve
-@pytest.mark.parametrize("fixture,tol", [("ico10k", 1e-4), ("ico10k", 1e-6), ("torus_mid", 1e-6)])
+@pytest.mark.parametrize("fixture,tol", [("ico10k", 1e-4), ("ico10k", 1e-6), ("torus_mid", 1e-6), ("cloud_mid", 1e-6)])
 def test_p3_solve_reaches_the_tolerance_like_the_reference(request, fixture, tol):
     p = request.getfixturevalue(fixture)
     solver = p.new_solver(tolerance=tol)
