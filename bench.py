@@ -371,8 +371,8 @@ def main():
     vcycle_bytes += info[-1]["rows"] ** 2 * 8
     roofline = {"bound": "hbm", "kernel": "spmv_staged_kernel<double,1,EPI_JACOBI,LANES> (fine level)" if args.kernel_path == 0 else "spmv_direct_kernel<double,1,EPI_JACOBI,LANES> (fine level)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": 121.3e6 if (world == 1 and n_side == 1000) else None,
-                "traffic_source": "profiles/r1_warm_traffic.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu, cache control off)",
+                "traffic": 114.6e6 if (world == 1 and n_side == 1000) else None,
+                "traffic_source": "profiles/r1_warm_traffic.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch of the fine-level sweep (ncu --cache-control none, mean of 8 launches: 104.6 MB read + 10.1 MB written; part of the 120 MB stays in the 126 MB L2 between sweeps)",
                 "algorithmic_bytes_per_launch": jac_bytes, "us_per_launch": jac_us,
                 "timing": "60 back-to-back launches of the kernel between two CUDA events on its launch stream (burst; peak = measured copy bandwidth)",
                 "us_per_launch_serialised_in_cycle": jac_us_in_cycle,
