@@ -113,6 +113,21 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                  "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
+// The same with an L2 eviction-priority hint for the source lines: hint 1 = evict_last (keep: the
+// operator is re-read by the next kernels), 2 = evict_first (streamed once per cycle).
+__device__ __forceinline__ uint64_t l2_policy(int hint) {
+    uint64_t p = 0;
+    if (hint == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else if (hint == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_copy_g2s_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_addr(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+        : "memory");
+}
 // Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute
 // starts while its predecessor in the stream drains; grid_dependency_wait() blocks until the
 // predecessor has completed and its writes are visible (no-ops for a normal launch).

@@ -32,6 +32,7 @@ struct DevMat {
     DeviceBuffer<long long> pair_off;   // product plan of the Galerkin step that fills this matrix
     DeviceBuffer<int2> pairs;           //   (sparse_kernels.h, build_spgemm_plan); empty: search per solve
     bool planned = false;
+    int l2_hint = 0;  // L2 eviction priority of this operator's slabs inside the cycle (sparse_kernels.cuh)
     // multi-GPU: the stored entries this rank computes in the Galerkin product ([e0, e1); all by default)
     // and, for the level operators, every rank's share (entry offsets, world + 1) for the all-gather
     int64_t e0 = 0, e1 = -1;
@@ -791,6 +792,22 @@ private:
             c.A.planned = true;
         }
         st_->transfer_timing["galerkin_plan_pairs"] = (double)plan_pairs;
+        // L2 residency of the cycle: the finest operator is read by six kernels per cycle (sweeps, residual,
+        // norm) and, with its vectors, fits the 126 MB L2 of a B200 when nothing else displaces it. Its slabs are
+        // fetched with evict_last, the once-per-cycle transfer operators of the finest level with evict_first.
+        {
+            int l2_bytes = 0, dev = 0;
+            GMG_CUDA(cudaGetDevice(&dev));
+            GMG_CUDA(cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, dev));
+            for (auto& l : lv_) l.A.l2_hint = l.P.l2_hint = l.R.l2_hint = 0;
+            if (n_levels_ > 0) {
+                const DevMat<T>& a0 = lv_[0].A;
+                const double rows = a0.plan.row_end >= 0 ? (double)(a0.plan.row_end - a0.plan.row_begin) / std::max(a0.rows, 1) : 1.0;
+                const double a_bytes = rows * ((double)a0.nnz * (sizeof(T) + 4) + (double)a0.rows * 4);
+                if (a_bytes <= 0.75 * l2_bytes) lv_[0].A.l2_hint = 1;
+                lv_[0].P.l2_hint = lv_[0].R.l2_hint = 2;
+            }
+        }
         upload_halos();
         coarse_.setup(lv_[n_levels_].n, stream_);
         GMG_CUDA(cudaStreamSynchronize(stream_));
@@ -1014,6 +1031,7 @@ private:
         a.n_rows = m.rows;
         a.ld = K_;
         a.rowptr = m.indptr.ptr, a.colidx = m.indices.ptr, a.vals = m.vals();
+        a.l2_hint = st_->l2_hints ? m.l2_hint : 0;
         a.omega = (T)st_->params.omega;
         a.ctl = ctl_.ptr;
         return a;

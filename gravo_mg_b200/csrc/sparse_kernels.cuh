@@ -126,6 +126,7 @@ struct SpmvArgs {
     double* hist_res = nullptr;
     double* hist_ms = nullptr;
     unsigned long long cond_handle = 0;
+    int l2_hint = 0;                   // staged: L2 eviction priority of the operator slabs (0 none, 1 keep, 2 stream)
     int n_early = 0;                   // staged: tiles [0, n_early) hold every row that is pushed or gathers halo
                                        // entries; the exchange is signalled once they are done (rest overlaps)
 };
@@ -317,6 +318,7 @@ __global__ void __launch_bounds__(TPB + 32) spmv_staged_kernel(const SpmvArgs<T>
         // requested right away: under programmatic dependent launch this CTA may start while the
         // previous kernel in the stream is still draining, and the copies overlap that tail.
         // Lane l prefetches the descriptor of tile iteration (32 * block + l); lane 0 issues.
+        const uint64_t policy = l2_policy(a.l2_hint);
         for (int it0 = 0; it0 < n_my; it0 += 32) {
             int4 mine = make_int4(0, 0, 0, 0);
             if (it0 + tid < n_my) mine = a.tile_desc[blockIdx.x + (it0 + tid) * gridDim.x];
@@ -340,10 +342,18 @@ __global__ void __launch_bounds__(TPB + 32) spmv_staged_kernel(const SpmvArgs<T>
                     const uint32_t n_rp = (uint32_t)(((d.y + 1 + 3) & ~3) - rp0);
                     const uint32_t cnt = (uint32_t)(d.w - d.z);
                     mbar_arrive_expect_tx(&full[s], n_rp * 4u + cnt * (uint32_t)(sizeof(T) + sizeof(int)));
-                    bulk_copy_g2s(rp, a.rowptr + rp0, n_rp * 4u, &full[s]);
-                    if (cnt) {
-                        bulk_copy_g2s(sv, a.vals + d.z, cnt * (uint32_t)sizeof(T), &full[s]);
-                        bulk_copy_g2s(sc, a.colidx + d.z, cnt * (uint32_t)sizeof(int), &full[s]);
+                    if (a.l2_hint) {
+                        bulk_copy_g2s_hint(rp, a.rowptr + rp0, n_rp * 4u, &full[s], policy);
+                        if (cnt) {
+                            bulk_copy_g2s_hint(sv, a.vals + d.z, cnt * (uint32_t)sizeof(T), &full[s], policy);
+                            bulk_copy_g2s_hint(sc, a.colidx + d.z, cnt * (uint32_t)sizeof(int), &full[s], policy);
+                        }
+                    } else {
+                        bulk_copy_g2s(rp, a.rowptr + rp0, n_rp * 4u, &full[s]);
+                        if (cnt) {
+                            bulk_copy_g2s(sv, a.vals + d.z, cnt * (uint32_t)sizeof(T), &full[s]);
+                            bulk_copy_g2s(sc, a.colidx + d.z, cnt * (uint32_t)sizeof(int), &full[s]);
+                        }
                     }
                 }
                 __syncwarp();
