@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--loop-mode", type=int, default=1)
     ap.add_argument("--kernel-path", type=int, default=0)
     ap.add_argument("--use-graph", type=int, default=1)
-    ap.add_argument("--l2-hints", type=int, default=1)
+    ap.add_argument("--l2-hints", type=int, default=0)
     ap.add_argument("--skip-exchange", type=int, default=0, help="measurement only: multi-GPU cycle without halo exchanges (wrong results)")
     ap.add_argument("--xfer-threads", type=int, default=-1, help="host threads staging caller buffers (-1 auto, 0 plain pageable copies)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

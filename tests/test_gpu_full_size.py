@@ -1,0 +1,101 @@
+"""BASELINE.json configurations at their full sizes, checked through size-independent properties
+(the oracle needs minutes at these sizes): the returned x satisfies the stopping criterion when
+the residual is recomputed on the host in fp64, residual histories are monotone, the columns of
+a multi-column solve are independent, a repeated solve reuses the staged pattern.
+
+  config 2  1 000 000-vertex torus, Poisson lhs = 1e-6 M + S, fp64, K = 1, 5 levels (lower_bound 500)
+  config 3  ~5 000 000-vertex torus (2236 x 2236), smoothing lhs = M + 1e-3 S, rhs = M V (K = 3), fp32 levels
+  config 5  ~2 000 000-vertex torus (1414 x 1414), conformal-flow style repeated solves, fp64, K = 3
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _mnorm_residual(lhs, rhs, x, m):
+    r = lhs @ x - rhs
+    return float(np.sqrt((m[:, None] * r * r).sum(0) / (m[:, None] * rhs * rhs).sum(0)).max())
+
+
+def _build(n_side):
+    from gravo_mg_b200 import synth
+
+    V, F = synth.torus_grid(n_side, n_side)
+    return synth.mesh_operators(V, F)
+
+
+def test_config2_poisson_1m_fp64():
+    import gravomg
+    from gravo_mg_b200 import synth
+
+    V, S, M, neigh = _build(1000)
+    lhs, rhs = synth.poisson_system(S, M)
+    s = gravomg.MultigridSolver(V, neigh, M, lower_bound=500, tolerance=1e-6)
+    x = s.solve(lhs, rhs)
+    t = s.solver_timing
+    assert [u.shape[0] for u in s.prolongation_matrices][0] == 1000000 and len(s.prolongation_matrices) == 4
+    m = M.diagonal()
+    res = _mnorm_residual(lhs, rhs, x, m)
+    assert res <= 1e-6 and abs(res - t["residue"]) <= 0.05 * res  # rounding floor of A x is ~3e-8 here
+    hist = [r for _, r in s.convergence]
+    assert len(hist) == int(t["iterations"]) <= 20 and all(a > b for a, b in zip(hist, hist[1:]))
+    assert s.residual(lhs, rhs, x) == pytest.approx(res, rel=0.05)
+    x2 = s.solve(lhs, rhs)  # staged pattern reused, same bits
+    np.testing.assert_array_equal(x, x2)
+    assert s.solver.transfer_timing()["pattern_reused"] == 1.0
+
+
+def test_config3_smoothing_5m_fp32_k3():
+    import gravomg
+    from gravo_mg_b200 import synth
+
+    V, S, M, neigh = _build(2236)
+    lhs, rhs = synth.smoothing_system(V, S, M)
+    assert rhs.shape == (2236 * 2236, 3)
+    s = gravomg.MultigridSolver(V, neigh, M, tolerance=1e-4, dtype="float32")
+    x = s.solve(lhs, rhs)
+    t = s.solver_timing
+    m = M.diagonal()
+    res = _mnorm_residual(lhs, rhs, x, m)  # judged in fp64 on the host
+    assert res <= 2e-4 and t["residue"] <= 1e-4, (res, t)
+    hist = [r for _, r in s.convergence]
+    assert all(a > b for a, b in zip(hist, hist[1:]))
+    # the three columns are independent solves: column 1 alone gives the same bits
+    s1 = gravomg.MultigridSolver(V, neigh, M, tolerance=1e-4, dtype="float32", max_iter=int(t["iterations"]))
+    s1.solver.set_option("tolerance", 0.0)  # same number of cycles as the K = 3 run
+    x1 = s1.solve(lhs, np.ascontiguousarray(rhs[:, 1]))
+    np.testing.assert_array_equal(x1[:, 0], x[:, 1])
+    # per-level achieved bandwidth (algorithmic bytes of the level's sweep / its chain time)
+    b = s.solver
+    for lvl, info in enumerate(b.level_info()[:-1]):
+        us = b.time_op("jacobi", lvl, 30)
+        gbs = (info["nnz_a"] * 8 + info["rows"] * (4 + 4 + 3 * 4 * 3)) / (us * 1e-6) / 1e9
+        print(f"\n[config 3] level {lvl}: {info['rows']} rows, sweep {us:.1f} us, {gbs:.0f} GB/s algorithmic")
+        assert us > 0
+
+
+def test_config5_repeated_solves_2m_fp64_k3():
+    import gravomg
+    from gravo_mg_b200 import synth, util
+
+    V, S, M, neigh = _build(1414)
+    s = gravomg.MultigridSolver(V, neigh, M, tolerance=1e-4)
+    Vt = V.copy()
+    m = M.diagonal()
+    iters = []
+    for step in range(6):
+        # demos/conformal_flow.py:54-59: M_t = mass(V_t) (here: the lumped mass rescaled, same pattern),
+        # lhs = M_t + 0.01 S, rhs = M_t V_t, V_{t+1} = normalize_area(solve)
+        Mt = M * (1.0 + 0.05 * step)
+        lhs = (Mt + 0.01 * S).tocsr()
+        rhs = Mt @ Vt
+        x = s.solve(lhs, rhs)
+        iters.append(int(s.solver_timing["iterations"]))
+        assert _mnorm_residual(lhs, rhs, x, m) <= 1e-4
+        if step:
+            assert s.solver.transfer_timing()["pattern_reused"] == 1.0
+        Vt = x / np.sqrt((x * x).sum(1).mean())
+    fresh = gravomg.MultigridSolver(V, neigh, M, tolerance=1e-4)
+    np.testing.assert_array_equal(fresh.solve(lhs, rhs), x)  # reuse changes nothing
+    assert max(iters) <= 12
