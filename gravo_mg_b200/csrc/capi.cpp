@@ -155,6 +155,7 @@ int gmg_set_option(gmg_handle h, const char* key, double value) {
         else if (k == "pdl") s.use_pdl = value != 0.0, cycle = true;
         else if (k == "fuse_norm") s.fuse_norm = value != 0.0, cycle = true;
         else if (k == "fuse_stop") s.fuse_stop = value != 0.0, cycle = true;
+        else if (k == "fp32_refine") s.fp32_refine = value != 0.0, cycle = true;
         else if (k == "l2_hints") s.l2_hints = value != 0.0, cycle = true;
         else if (k == "tail_rows") s.tail_rows = (int)value, cycle = true;
         else if (k == "dist_graph") s.dist_graph = value != 0.0, cycle = true;
@@ -200,6 +201,7 @@ int gmg_get_option(gmg_handle h, const char* key, double* value) {
         else if (k == "pdl") *value = s.use_pdl;
         else if (k == "fuse_norm") *value = s.fuse_norm;
         else if (k == "fuse_stop") *value = s.fuse_stop;
+        else if (k == "fp32_refine") *value = s.fp32_refine;
         else if (k == "l2_hints") *value = s.l2_hints;
         else if (k == "tail_rows") *value = s.tail_rows;
         else if (k == "dist_graph") *value = s.dist_graph;

@@ -19,7 +19,7 @@
 namespace gmg {
 namespace {
 
-enum OpKind { OP_JACOBI = 0, OP_RESIDUAL = 1, OP_RESTRICT = 2, OP_PROLONG = 3, OP_NORM = 4, OP_COARSE = 5, OP_ZERO = 6, OP_TAIL = 7, OP_HALO = 8, OP_ALLGATHER = 9, OP_KINDS = 10 };
+enum OpKind { OP_JACOBI = 0, OP_RESIDUAL = 1, OP_RESTRICT = 2, OP_PROLONG = 3, OP_NORM = 4, OP_COARSE = 5, OP_ZERO = 6, OP_TAIL = 7, OP_HALO = 8, OP_ALLGATHER = 9, OP_REFINE = 10, OP_KINDS = 11 };
 constexpr int kMaxLevels = 16;
 
 // CSR matrix on the device. Setup arithmetic (Galerkin products, factorisation) is always
@@ -240,7 +240,7 @@ public:
         const auto t0 = std::chrono::steady_clock::now();
         const size_t count = (size_t)st_->n * K_;
         if (st_->dist.sharded(0)) allgather_rows(0, x_final_, stream_);
-        if (sizeof(T) == 4) launch_cast_f32_f64(reinterpret_cast<const float*>(x_final_), x64_.ptr, count, stream_);
+        if (sizeof(T) == 4 && !refine()) launch_cast_f32_f64(reinterpret_cast<const float*>(x_final_), x64_.ptr, count, stream_);
         const double* src = sizeof(T) == 4 ? x64_.ptr : reinterpret_cast<const double*>(x_final_);
         if (HostTransfer* xf = transfer()) {
             GMG_CUDA(cudaStreamSynchronize(stream_));
@@ -936,6 +936,7 @@ private:
         rhs64_.ensure((size_t)st_->n * K_);
         if (max_halo_ && !use_p2p()) halo_send_.ensure(max_halo_ * K_), halo_recv_.ensure(max_halo_ * K_);
         if (sizeof(T) == 4) {
+            r64_.ensure((size_t)st_->n * K_);
             x64_.ensure((size_t)st_->n * K_);
             const size_t nc = (size_t)lv_[n_levels_].n * K_;
             coarse_b64_.ensure(nc), coarse_x64_.ensure(nc);
@@ -1019,11 +1020,20 @@ private:
         if (sizeof(T) == 8) {
             GMG_CUDA(cudaMemcpyAsync(lv_[0].b.ptr, rhs64_.ptr, count * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
             GMG_CUDA(cudaMemcpyAsync(lv_[0].x.ptr, rhs64_.ptr, count * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+        } else if (refine()) {
+            // mixed precision: the iterate lives in fp64 (x0 = rhs); the prologue forms its defect for the fp32 levels
+            GMG_CUDA(cudaMemcpyAsync(x64_.ptr, rhs64_.ptr, count * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
         } else {
             launch_cast_f64_f32(rhs64_.ptr, reinterpret_cast<float*>(lv_[0].b.ptr), count, stream_);
             launch_cast_f64_f32(rhs64_.ptr, reinterpret_cast<float*>(lv_[0].x.ptr), count, stream_);
         }
     }
+
+    // fp32 levels as the correction scheme of an fp64 iterate (defect correction): per cycle
+    //     e = V-cycle_fp32(A, r) from a zero guess;  x += e (fp64);  r = b - A x (fp64 values, fp64 x)
+    // and the stopping norm is the norm of that fp64 defect. Without it a cycle that carries x in fp32
+    // stalls at the fp32 rounding floor of A x (1.7e-3 relative on BASELINE config 3, 5 M vertices).
+    bool refine() const { return sizeof(T) == 4 && n_levels_ > 0 && st_->fp32_refine; }
 
     // ---- the V-cycle as a launch list ----------------------------------------------------
     SpmvArgs<T> base_args(const DevMat<T>& m) const {
@@ -1161,6 +1171,18 @@ private:
             Op op;
             op.kind = OP_COARSE, op.level = 0;
             ops_.push_back(op);
+        } else if (refine()) {
+            if (st_->dist.world > 1) throw std::invalid_argument("float32 levels (mixed-precision refinement) are single-GPU for now; use dtype float64 on several GPUs");
+            Op pr;  // prologue: defect of the initial guess, no correction to add, no stopping test
+            pr.kind = OP_REFINE, pr.level = -1;
+            prologue_.push_back(pr);
+            Op z;
+            z.kind = OP_ZERO, z.level = 0, z.zero_ptr = cur, z.zero_bytes = (size_t)lv_[0].n * K_ * sizeof(T);
+            ops_.push_back(z);
+            push_vcycle(0, cur, alt, 0, false);
+            Op rf;  // x += e, new defect, stopping test
+            rf.kind = OP_REFINE, rf.level = 0, rf.vec = cur;
+            ops_.push_back(rf);
         } else if (!fused) {
             push_vcycle(0, cur, alt, 0, false);
         } else {
@@ -1174,7 +1196,8 @@ private:
         }
         if (tail_level_ > 0 && tail_end_ > tail_begin_) collapse_tail();
         x_final_ = cur;
-        if (n_levels_ > 0) push_halo(0, HALO_A, cur);
+        if (n_levels_ > 0 && !refine()) push_halo(0, HALO_A, cur);
+        if (!refine())
         {   // residualCheck(LHS, b, x, stoppingCriteria) (multigrid_solver.cpp:1413)
             Op op;
             op.kind = OP_NORM, op.level = 0, op.epi = fused ? EPI_NORMJAC : EPI_NORM, op.plan = &lv_[0].A.plan;
@@ -1371,6 +1394,40 @@ private:
                     if (op.vec2) allgather_rows(op.level, op.vec2, s);
                 }
                 break;
+            case OP_REFINE: {
+                const size_t count = (size_t)st_->n * K_;
+                if (op.level >= 0) launch_add_f32_to_f64(reinterpret_cast<const float*>(op.vec), x64_.ptr, count, s), ++launches;
+                SpmvPlan plan;  // fp64 defect straight from global memory (the row tiles are sized for fp32 slabs)
+                plan.path = 1, plan.lanes = lv_[0].A.plan.lanes;
+                SpmvArgs<double> a;
+                a.n_rows = lv_[0].n, a.ld = K_;
+                a.rowptr = lv_[0].A.indptr.ptr, a.colidx = lv_[0].A.indices.ptr, a.vals = lv_[0].A.v64.ptr;
+                a.weight = p.stopping_criteria == 2 ? mass_.ptr : p.stopping_criteria == 1 ? minv_.ptr : nullptr;
+                a.ctl = ctl_.ptr;
+                const bool test = op.level >= 0;
+                const bool fused_test = test && K_ <= kMaxRhsTile && st_->fuse_stop;
+                if (fused_test) {
+                    a.fin_ticket = tail_bar_.ptr + 2;
+                    a.hist_res = hist_res_.ptr, a.hist_ms = hist_ms_.ptr, a.cond_handle = cond;
+                }
+                NormChunks chunks;
+                for (int k0 = 0; k0 < K_; k0 += kMaxRhsTile) {
+                    const int kt = std::min(kMaxRhsTile, K_ - k0);
+                    a.x = x64_.ptr + k0, a.b = rhs64_.ptr + k0, a.out = r64_.ptr + k0;
+                    a.partials = partials_.ptr + (size_t)chunks.n_chunks * kNormChunkStride;
+                    chunks.kt[chunks.n_chunks] = kt;
+                    chunks.n_blocks[chunks.n_chunks] = launch_spmv<double>(EPI_RESNORM, kt, a, plan, s);
+                    ++chunks.n_chunks;
+                    ++launches;
+                }
+                launch_cast_f64_f32(r64_.ptr, reinterpret_cast<float*>(lv_[0].b.ptr), count, s);
+                ++launches;
+                if (test && !fused_test) {
+                    launch_norm_finalize(partials_.ptr, chunks, ctl_.ptr, hist_res_.ptr, hist_ms_.ptr, 1, cond, s);
+                    ++launches;
+                }
+                break;
+            }
             case OP_TAIL: {
                 const int sms = tail_grid();
                 tail_kernel<T><<<sms, kTailThreads, 0, s>>>(reinterpret_cast<const TailOp<T>*>(tail_table_.ptr), n_tail_ops_, tail_bar_.ptr);
@@ -1548,7 +1605,7 @@ private:
     DenseCoarseSolver coarse_;
     DeviceBuffer<CycleControl> ctl_;
     CycleControl* ctl_host_ = nullptr;
-    DeviceBuffer<double> hist_res_, hist_ms_, partials_, mass_, minv_, rhs64_, x64_, coarse_b64_, coarse_x64_, io64_;
+    DeviceBuffer<double> hist_res_, hist_ms_, partials_, mass_, minv_, rhs64_, x64_, r64_, coarse_b64_, coarse_x64_, io64_;
     DeviceBuffer<double> rho_, weights64_;
     DeviceBuffer<unsigned long long> trace_buf_;
     DeviceBuffer<T> weights_;

@@ -61,6 +61,7 @@ struct SolverState {
     bool p2p_fuse = true;            // p2p: pushes fused into the producing kernels, waits into the consuming ones
     bool l2_hints = false;           // L2 eviction-priority hints on the operator slabs of the finest level (evict_last for
                                      // A_0, evict_first for U_0 / U_0^T); measured on config 2: no effect (263.7 us per cycle either way)
+    bool fp32_refine = true;         // dtype float32: the fp32 cycle corrects an fp64 iterate (fp64 defect and stopping norm)
     bool fuse_stop = true;           // single GPU, K <= 4: the norm kernel's last CTA applies the stopping rule (no finalize kernel)
     bool fuse_norm = true;           // stopping test fused with the next cycle's first sweep
     bool use_pdl = true;             // programmatic dependent launch of the row-product kernels

@@ -150,6 +150,9 @@ __global__ void smoother_weights_kernel(const double* __restrict__ rho, int n_le
 __global__ void cast_f64_f32_kernel(const double* __restrict__ s, float* __restrict__ d, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = (float)s[i];
 }
+__global__ void add_f32_to_f64_kernel(const float* __restrict__ e, double* __restrict__ x, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] += (double)e[i];
+}
 __global__ void cast_f32_f64_kernel(const float* __restrict__ s, double* __restrict__ d, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = (double)s[i];
 }
@@ -322,7 +325,7 @@ int launch_staged(SpmvArgs<T>& a, const SpmvPlan& plan, cudaStream_t stream) {
     auto kernel = spmv_staged_kernel<T, K, EPI, LANES>;
     const int per_sm = resident_blocks((const void*)kernel, kStagedThreads + 32, smem);
     int grid = std::min(std::max(plan.n_tiles, 1), per_sm * num_sms());
-    if (EPI == EPI_NORM || EPI == EPI_NORMJAC) grid = std::min(grid, kMaxNormBlocks);
+    if (EPI == EPI_NORM || EPI == EPI_NORMJAC || EPI == EPI_RESNORM) grid = std::min(grid, kMaxNormBlocks);
     if (!g_dry_run) launch_pdl(kernel, grid, kStagedThreads + 32, smem, stream, a);
     return grid;
 }
@@ -347,7 +350,7 @@ int launch_one(SpmvArgs<T>& a, const SpmvPlan& plan, cudaStream_t stream) {
         const int rows_per_block = kDirectThreads / plan.lanes;
         const int64_t want = ((int64_t)(a.n_rows - a.row_begin) + rows_per_block - 1) / rows_per_block;
         grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)num_sms() * 32);
-        if (EPI == EPI_NORM || EPI == EPI_NORMJAC) grid = std::min(grid, kMaxNormBlocks);
+        if (EPI == EPI_NORM || EPI == EPI_NORMJAC || EPI == EPI_RESNORM) grid = std::min(grid, kMaxNormBlocks);
         if (g_dry_run) return grid;
         switch (plan.lanes) {
             case 1: launch_pdl(spmv_direct_kernel<T, K, EPI, 1>, grid, kDirectThreads, 0, stream, a); break;
@@ -371,6 +374,7 @@ int launch_k(int epi, SpmvArgs<T>& a, const SpmvPlan& plan, cudaStream_t stream)
         case EPI_ADD: return launch_one<T, K, EPI_ADD>(a, plan, stream);
         case EPI_NORM: return launch_one<T, K, EPI_NORM>(a, plan, stream);
         case EPI_NORMJAC: return launch_one<T, K, EPI_NORMJAC>(a, plan, stream);
+        case EPI_RESNORM: return launch_one<T, K, EPI_RESNORM>(a, plan, stream);
     }
     throw std::invalid_argument("unknown epilogue");
 }
@@ -462,6 +466,11 @@ void launch_cast_f64_f32(const double* src, float* dst, size_t n, cudaStream_t s
 void launch_cast_f32_f64(const float* src, double* dst, size_t n, cudaStream_t stream) {
     if (!n) return;
     cast_f32_f64_kernel<<<stream_grid(n), 256, 0, stream>>>(src, dst, n);
+    GMG_CUDA(cudaGetLastError());
+}
+void launch_add_f32_to_f64(const float* e, double* x, size_t n, cudaStream_t stream) {
+    if (!n) return;
+    add_f32_to_f64_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, stream>>>(e, x, n);
     GMG_CUDA(cudaGetLastError());
 }
 void launch_expand_rows(int n_rows, const int* rowptr, int* rowidx, cudaStream_t stream) {

@@ -9,6 +9,8 @@
 //   EPI_RESIDUAL  out_i = b_i - acc_i                                   (:1066)
 //   EPI_ADD       out_i = xin_i + acc_i                                 x += U e (:1082)
 //   EPI_NORM      partial sums of w_i (acc_i - b_i)^2 and w_i b_i^2     residualCheck (:1228-1277)
+//   EPI_RESNORM   EPI_NORM and EPI_RESIDUAL from the same row product: the fp64 defect of the
+//                 mixed-precision cycle (fp32 levels correct an fp64 iterate) and its stopping norm
 //   EPI_NORMJAC   EPI_NORM and EPI_JACOBI from the same row product: the stopping test of one
 //                 cycle and the first pre-smoothing sweep of the next both need b - A x
 //
@@ -29,7 +31,7 @@
 
 namespace gmg {
 
-enum Epilogue { EPI_SPMV = 0, EPI_JACOBI = 1, EPI_RESIDUAL = 2, EPI_ADD = 3, EPI_NORM = 4, EPI_NORMJAC = 5 };
+enum Epilogue { EPI_SPMV = 0, EPI_JACOBI = 1, EPI_RESIDUAL = 2, EPI_ADD = 3, EPI_NORM = 4, EPI_NORMJAC = 5, EPI_RESNORM = 6 };
 
 // Device-resident loop state of one solve (multigrid_solver.cpp:1411-1417).
 struct CycleControl {
@@ -217,7 +219,7 @@ __device__ __forceinline__ void load_row_operands(const SpmvArgs<T>& a, int row,
         const T om = a.omega_ptr ? *a.omega_ptr : a.omega;
         r.scale = om * a.dinv[row];
     }
-    if (EPI == EPI_JACOBI || EPI == EPI_RESIDUAL || EPI == EPI_NORM || EPI == EPI_NORMJAC) {
+    if (EPI == EPI_JACOBI || EPI == EPI_RESIDUAL || EPI == EPI_NORM || EPI == EPI_NORMJAC || EPI == EPI_RESNORM) {
 #pragma unroll
         for (int k = 0; k < K; ++k) r.b[k] = a.b[o + k];
     }
@@ -229,7 +231,7 @@ __device__ __forceinline__ void load_row_operands(const SpmvArgs<T>& a, int row,
 #pragma unroll
         for (int k = 0; k < K; ++k) r.xo[k] = a.xin[o + k];
     }
-    if (EPI == EPI_NORM || EPI == EPI_NORMJAC) r.w = a.weight ? a.weight[row] : 1.0;
+    if (EPI == EPI_NORM || EPI == EPI_NORMJAC || EPI == EPI_RESNORM) r.w = a.weight ? a.weight[row] : 1.0;
 }
 
 template <typename T, int K, int EPI>
@@ -249,7 +251,7 @@ __device__ __forceinline__ void row_epilogue(const SpmvArgs<T>& a, int row, cons
         }
         if (a.send_mask && !a.push_out2) peer_push_row<T, K>(a, a.out, row, acc);
     }
-    if (EPI == EPI_NORM || EPI == EPI_NORMJAC) {
+    if (EPI == EPI_NORM || EPI == EPI_NORMJAC || EPI == EPI_RESNORM) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const double bk = (double)r.b[k];
@@ -262,7 +264,7 @@ __device__ __forceinline__ void row_epilogue(const SpmvArgs<T>& a, int row, cons
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             if (EPI == EPI_JACOBI || EPI == EPI_NORMJAC) res[k] = r.xo[k] + r.scale * (r.b[k] - acc[k]);
-            else if (EPI == EPI_RESIDUAL) res[k] = r.b[k] - acc[k];
+            else if (EPI == EPI_RESIDUAL || EPI == EPI_RESNORM) res[k] = r.b[k] - acc[k];
             else res[k] = r.xo[k] + acc[k];  // EPI_ADD
         }
 #pragma unroll
@@ -424,7 +426,7 @@ __global__ void __launch_bounds__(TPB + 32) spmv_staged_kernel(const SpmvArgs<T>
             }
         }
     }
-    if (EPI == EPI_NORM || EPI == EPI_NORMJAC) {
+    if (EPI == EPI_NORM || EPI == EPI_NORMJAC || EPI == EPI_RESNORM) {
         block_sum_store<2 * K, TPB + 32>(nrm, a.partials + (size_t)blockIdx.x * 2 * K);
         if (a.fin_ticket)
             fused_stopping_test<K>(a.partials, a.fin_ticket, const_cast<CycleControl*>(a.ctl), a.hist_res, a.hist_ms, a.cond_handle);
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__(kDirectThreads) spmv_direct_kernel(const SpmvA
             row_epilogue<T, K, EPI>(a, row, acc, ops, nrm);
         }
     }
-    if (EPI == EPI_NORM || EPI == EPI_NORMJAC) {
+    if (EPI == EPI_NORM || EPI == EPI_NORMJAC || EPI == EPI_RESNORM) {
         block_sum_store<2 * K, TPB>(nrm, a.partials + (size_t)blockIdx.x * 2 * K);
         if (a.fin_ticket)
             fused_stopping_test<K>(a.partials, a.fin_ticket, const_cast<CycleControl*>(a.ctl), a.hist_res, a.hist_ms, a.cond_handle);

@@ -71,6 +71,7 @@ void launch_smoother_weights(const double* rho, int n_levels, int pre, int post,
                              T* weights, double* weights64, cudaStream_t stream);
 void launch_cast_f64_f32(const double* src, float* dst, size_t n, cudaStream_t stream);
 void launch_cast_f32_f64(const float* src, double* dst, size_t n, cudaStream_t stream);
+void launch_add_f32_to_f64(const float* e, double* x, size_t n, cudaStream_t stream);  // x += e
 void launch_expand_rows(int n_rows, const int* rowptr, int* rowidx, cudaStream_t stream);
 // C = A * B on an existing sorted pattern of C, one thread per stored entry of C, products
 // added in the order of A's row (the order a row-wise CPU Gustavson pass uses).
