@@ -736,11 +736,12 @@ private:
             lv_[k].R.upload_values(r.data.data(), stream_);
             lv_[k].R.refresh_cast(stream_);
             range(k + 1, d.sharded(k), b, e);  // rows of R are coarse points; sharded with the fine level
+            const int lanes_r = st_->staged_lanes_r ? st_->staged_lanes_r : st_->staged_lanes;
             if (d.sharded(k)) {  // restriction: rows of level k + 1, gathers r_k, writes b_{k+1} and the first x_{k+1}
                 const std::vector<char> early = early_rows(r, k + 1, k, {{HALO_A, k + 1}});
-                lv_[k].R.make_plan(r.indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e, &early);
+                lv_[k].R.make_plan(r.indptr, st_->kernel_path, lanes_r, stream_, b, e, &early);
             } else
-                lv_[k].R.make_plan(r.indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e);
+                lv_[k].R.make_plan(r.indptr, st_->kernel_path, lanes_r, stream_, b, e);
             lv_[k].AP.upload_pattern(st_->ap_pat[k], stream_);
             lv_[k].AP.make_rowidx(stream_);
         }

@@ -33,6 +33,9 @@ def main():
     s = gravomg.MultigridSolver(V, neigh, M, lower_bound=500, tolerance=1e-6, device=local)
     b = s.solver
     b.set_option("loop_mode", 1)
+    for kv in os.environ.get("GMG_OPTIONS", "").split(","):  # e.g. GMG_OPTIONS=lanes_r=4,l2_hints=1
+        if "=" in kv:
+            b.set_option(kv.split("=")[0], float(kv.split("=")[1]))
     if world > 1:
         s.distribute()
     for _ in range(3):
