@@ -767,7 +767,7 @@ private:
             // A_{k+1} in this rank's coarse range and the rows of A_k U_k those need (own fine range plus
             // the rows its restriction gathers); the level operator is all-gathered per solve
             f.AP.e0 = 0, f.AP.e1 = f.AP.nnz, c.A.e0 = 0, c.A.e1 = c.A.nnz, c.A.share.clear();
-            if (d.sharded(k) && (st_->dist_shard_setup > 0 || (st_->dist_shard_setup < 0 && d.world >= 4))) {
+            if (d.sharded(k) && (st_->dist_shard_setup > 0 || (st_->dist_shard_setup < 0 && d.world >= 8))) {
                 const HostCsr& r = st_->r_host[k];
                 const HostCsr& ap = st_->ap_pat[k];
                 const HostCsr& ac = st_->a_pat[k + 1];

@@ -56,8 +56,9 @@ struct SolverState {
     bool p2p = true;                 // multi-GPU: halos and norms through NVLink peer memory (peer_exchange.h);
                                      // false: pack / ncclSend / ncclRecv / unpack and ncclAllReduce
     int dist_shard_setup = -1;       // multi-GPU: sharded levels compute only their share of the Galerkin product and the
-                                     // values are all-gathered (NCCL). -1: from 4 ranks on (measured: at 2 ranks the two
-                                     // all-gathers cost more than the halved products save), 0 replicated, 1 sharded
+                                     // values are all-gathered (NCCL). -1: from 8 ranks on, 0 replicated, 1 sharded. Measured
+                                     // reduction per solve, replicated -> sharded: 0.66 -> 0.76 ms at 2 ranks, 1.22 -> 1.43 ms
+                                     // at 4: the NCCL all-gathers of the level values cost more than the products save
     bool dist_skip_exchange = false; // measurement only: drop the halo exchanges of the cycle (results are wrong)
     bool p2p_fuse = true;            // p2p: pushes fused into the producing kernels, waits into the consuming ones
     bool l2_hints = false;           // L2 eviction-priority hints on the operator slabs of the finest level (evict_last for
