@@ -43,7 +43,7 @@ struct SolverState {
     std::vector<double> mass_diag;   // lumped mass (constructor argument)
     Hierarchy hier;                  // U[k] and the debug arrays
     bool use_graph = true;
-    int loop_mode = 0;               // 0 host loop (one sync per cycle), 1 device while-graph
+    int loop_mode = 1;               // 1 device while-graph (the whole cycle loop is one launch), 0 host loop (one sync per cycle)
     int kernel_path = 0;             // 0 staged (TMA) where it fits, 1 direct everywhere
     int staged_lanes_r = 0;          // the same for the restriction operators U^T only (0 = follow staged_lanes)
     int staged_lanes = 0;            // staged kernels: threads per row; 0 = from the mean row length
