@@ -130,6 +130,8 @@ public:
         if (st->params.device < 0 || st->params.device >= count) throw std::invalid_argument("invalid CUDA device ordinal");
         GMG_CUDA(cudaSetDevice(st->params.device));
         GMG_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+        GMG_CUDA(cudaStreamCreateWithFlags(&stream2_, cudaStreamNonBlocking));
+        GMG_CUDA(cudaEventCreateWithFlags(&rhs_ready_, cudaEventDisableTiming));
         for (auto& e : ev_) GMG_CUDA(cudaEventCreate(&e));
         ctl_.ensure(2);
         GMG_CUDA(cudaMemsetAsync(ctl_.ptr, 0, 2 * sizeof(CycleControl), stream_));
@@ -159,6 +161,8 @@ public:
         for (auto& e : ev_) cudaEventDestroy(e);
         for (auto& e : prof_events_) cudaEventDestroy(e);
         if (ctl_host_) cudaFreeHost(ctl_host_);
+        if (rhs_ready_) cudaEventDestroy(rhs_ready_);
+        if (stream2_) cudaStreamDestroy(stream2_);
         if (stream_) cudaStreamDestroy(stream_);
     }
 
@@ -217,7 +221,15 @@ public:
             }
         }
         numeric_ready_ = false;
-        if (wait || !xf) GMG_CUDA(cudaStreamSynchronize(stream_));
+        if (xf) {
+            GMG_CUDA(cudaEventRecord(rhs_ready_, stream2_));
+            rhs_pending_ = true;
+        }
+        if (wait || !xf) {
+            GMG_CUDA(cudaStreamSynchronize(stream_));
+            GMG_CUDA(cudaStreamSynchronize(stream2_));
+            rhs_pending_ = false;
+        }
         staged_ = true;
         auto& tt = st_->transfer_timing;
         tt["stage_host_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -230,7 +242,9 @@ public:
     std::vector<HostTransfer::Copy> value_copies(const double* data, const double* rhs, int64_t nnz, int64_t n, int K) {
         std::vector<HostTransfer::Copy> c(2);
         c[0].dev = lv_[0].A.v64.ptr, c[0].host = data, c[0].bytes = (size_t)nnz * sizeof(double);
-        c[1].dev = rhs64_.ptr, c[1].host = rhs, c[1].bytes = (size_t)n * K * sizeof(double);
+        // the right-hand side is not needed before the cycles start: it travels on a second stream so
+        // the Galerkin reduction and the coarse factor begin as soon as the matrix values have arrived
+        c[1].dev = rhs64_.ptr, c[1].host = rhs, c[1].bytes = (size_t)n * K * sizeof(double), c[1].stream = stream2_;
         return c;
     }
 
@@ -272,10 +286,14 @@ public:
 
         GMG_CUDA(cudaMemsetAsync(ctl_.ptr, 0, sizeof(CycleControl), stream_));
         GMG_CUDA(cudaEventRecord(ev_[0], stream_));
+        launches += setup_numeric(ev_[1]);
         // x0 = rhs (core.cpp:69), b = rhs
+        if (rhs_pending_) {
+            GMG_CUDA(cudaStreamWaitEvent(stream_, rhs_ready_, 0));
+            rhs_pending_ = false;
+        }
         set_initial_guess();
         launches += sizeof(T) == 4 ? 2 : 0;
-        launches += setup_numeric(ev_[1]);
         GMG_CUDA(cudaEventRecord(ev_[2], stream_));
 
         // ---- "cycles" (multigrid_solver.cpp:1411-1417)
@@ -1034,7 +1052,7 @@ private:
     //     e = V-cycle_fp32(A, r) from a zero guess;  x += e (fp64);  r = b - A x (fp64 values, fp64 x)
     // and the stopping norm is the norm of that fp64 defect. Without it a cycle that carries x in fp32
     // stalls at the fp32 rounding floor of A x (1.7e-3 relative on BASELINE config 3, 5 M vertices).
-    bool refine() const { return sizeof(T) == 4 && n_levels_ > 0 && st_->fp32_refine; }
+    bool refine() const { return sizeof(T) == 4 && n_levels_ > 0 && st_->fp32_refine && st_->dist.world <= 1; }
 
     // ---- the V-cycle as a launch list ----------------------------------------------------
     SpmvArgs<T> base_args(const DevMat<T>& m) const {
@@ -1173,7 +1191,6 @@ private:
             op.kind = OP_COARSE, op.level = 0;
             ops_.push_back(op);
         } else if (refine()) {
-            if (st_->dist.world > 1) throw std::invalid_argument("float32 levels (mixed-precision refinement) are single-GPU for now; use dtype float64 on several GPUs");
             Op pr;  // prologue: defect of the initial guess, no correction to add, no stopping test
             pr.kind = OP_REFINE, pr.level = -1;
             prologue_.push_back(pr);
@@ -1598,7 +1615,9 @@ private:
 
     SolverState* st_;
     std::unique_ptr<HostTransfer> xfer_;
-    cudaStream_t stream_ = nullptr;
+    cudaStream_t stream_ = nullptr, stream2_ = nullptr;
+    cudaEvent_t rhs_ready_ = nullptr;
+    bool rhs_pending_ = false;
     cudaEvent_t ev_[4] = {};
     std::vector<Level> lv_;
     int n_levels_ = 0;

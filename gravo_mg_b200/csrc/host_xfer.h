@@ -63,6 +63,7 @@ public:
         void* dev;
         const void* host;
         size_t bytes;
+        cudaStream_t stream = nullptr;  // nullptr: the stream passed to upload_and_compare
     };
     struct Compare {
         const void* a;
@@ -105,8 +106,9 @@ public:
             if (w.used[slot]) GMG_CUDA(cudaEventSynchronize(w.ev[slot]));
             char* pin = w.pinned + (size_t)slot * kChunk;
             std::memcpy(pin, (const char*)c.host + k.offset, k.bytes);
-            GMG_CUDA(cudaMemcpyAsync((char*)c.dev + k.offset, pin, k.bytes, cudaMemcpyHostToDevice, stream));
-            GMG_CUDA(cudaEventRecord(w.ev[slot], stream));
+            cudaStream_t cs = c.stream ? c.stream : stream;
+            GMG_CUDA(cudaMemcpyAsync((char*)c.dev + k.offset, pin, k.bytes, cudaMemcpyHostToDevice, cs));
+            GMG_CUDA(cudaEventRecord(w.ev[slot], cs));
             w.used[slot] = true;
         });
         return equal.load();
