@@ -86,7 +86,15 @@ const char* gmg_last_error(gmg_handle h);
  * test and next cycle's first sweep in one kernel), "tail_rows" (levels with at most this many
  * rows run inside one persistent kernel with grid barriers; 0 = one kernel per operator), "profile" (0/1 per-kernel
  * event timing), "xfer_threads" (host threads that stage caller-owned buffers through pinned chunks during
- * gmg_solve / gmg_stage_system / gmg_fetch_solution; -1 = auto, 0 = plain pageable copies). */
+ * gmg_solve / gmg_stage_system / gmg_fetch_solution; -1 = auto, 0 = plain pageable copies),
+ * "fuse_stop" (0/1 the norm kernel's last CTA applies the stopping rule), "spgemm_plan" (0/1 Galerkin
+ * products from per-pattern index-pair lists), "coarse_dataflow" (0/1 coarse factor as one tile-task kernel),
+ * "fp32_refine" (0/1 float32 levels correct an fp64 iterate with an fp64 defect), "lanes_r" (threads per row
+ * of the restriction operators), "l2_hints" (0/1 L2 eviction-priority hints on the finest operators),
+ * "trace" (0/1 device timeline, gmg_get_trace); multi-GPU: "p2p" (1 halo rows through NVLink peer memory,
+ * 0 NCCL send/recv), "p2p_fuse" (0/1 pushes and waits fused into the row-product kernels), "dist_graph",
+ * "dist_shard_setup" (-1 auto, 0 replicated, 1 sharded Galerkin reduction), "dist_skip_exchange"
+ * (measurement only). Unknown keys fail. */
 int gmg_set_option(gmg_handle h, const char* key, double value);
 int gmg_get_option(gmg_handle h, const char* key, double* value);
 

@@ -102,3 +102,20 @@ def test_product_does_not_import_the_oracle():
                 text = open(os.path.join(base, name), errors="replace").read()
                 for needle in ("import oracle", "from oracle", "gravomg_oracle", "oracle/", "orc_"):
                     assert needle not in text, f"{name} refers to the oracle ({needle!r})"
+
+
+def test_options_round_trip_without_a_device(ico_small):
+    """Every documented option key is accepted and read back (host only: no engine is created)."""
+    b = ico_small.new_solver().solver
+    keys = {"tolerance": 1e-5, "stopping_criteria": 0, "pre_iters": 3, "post_iters": 1, "max_iter": 7, "omega": 0.5,
+            "smoother": 0, "cheb_alpha": 8.0, "use_graph": 0, "loop_mode": 0, "kernel_path": 1, "lanes": 4, "lanes_r": 8,
+            "pdl": 0, "fuse_norm": 0, "fuse_stop": 0, "tail_rows": 1000, "profile": 1, "trace": 1, "xfer_threads": 3,
+            "spgemm_plan": 0, "coarse_dataflow": 0, "fp32_refine": 0, "l2_hints": 1, "p2p": 0, "p2p_fuse": 0,
+            "dist_graph": 0, "dist_shard_setup": 1, "dist_skip_exchange": 1}
+    for k, v in keys.items():
+        b.set_option(k, v)
+        assert b.get_option(k) == pytest.approx(v), k
+    with pytest.raises(RuntimeError, match="unknown option"):
+        b.set_option("no_such_option", 1)
+    with pytest.raises(RuntimeError):
+        b.set_option("lanes", 3)
