@@ -148,7 +148,7 @@ int gmg_set_option(gmg_handle h, const char* key, double value) {
         else if (k == "cheb_alpha") s.params.cheb_alpha = value, cycle = true;
         else if (k == "lanes") s.staged_lanes = (int)value, hierarchy = true;
         else if (k == "lanes_r") s.staged_lanes_r = (int)value, hierarchy = true;
-        else if (k == "cycle_type") s.params.cycle_type = (int)value;
+        else if (k == "cycle_type") s.params.cycle_type = (int)value, cycle = true;
         else if (k == "use_graph") s.use_graph = value != 0.0;
         else if (k == "loop_mode") s.loop_mode = (int)value;
         else if (k == "profile") s.profile = value != 0.0;

@@ -273,7 +273,8 @@ public:
         if (!staged_) throw std::logic_error("solve_staged before stage_system");
         set_launch_pdl(st_->use_pdl);
         const gmg_params& p = st_->params;
-        if (p.cycle_type != 0) throw std::invalid_argument("only cycle_type 0 (V-cycle) is implemented on the device path");
+        if (p.cycle_type < 0 || p.cycle_type > 2) throw std::invalid_argument("cycle_type must be 0 (V), 1 (F) or 2 (W)");
+        if (p.cycle_type != 0 && st_->dist.world > 1) throw std::invalid_argument("F- and W-cycles are single-GPU for now");
         if (p.max_iter < 1) throw std::invalid_argument("max_iter must be >= 1");
         if (p.stopping_criteria < 0 || p.stopping_criteria > 3) throw std::invalid_argument("stopping_criteria must be 0..3");
         if (hist_res_.count < (size_t)p.max_iter) {
@@ -1096,73 +1097,81 @@ private:
         }
     }
 
-    // multiGridVCycleGS (multigrid_solver.cpp:1059-1088) at level k. `cur` holds x_k on entry and
-    // on exit; `pre_done` sweeps were already applied by the caller (zero-guess shortcut).
-    void push_vcycle(int k, T*& cur, T*& alt, int pre_done, bool fused_top) {
+    // One cycle at level k: multiGridVCycleGS (multigrid_solver.cpp:1059-1088; type 0), multiGridFCycleGS
+    // (:1091-1140; type 1) or multiGridWCycleGS (:1143-1192; type 2). `cur` holds x_k on entry and on exit;
+    // `pre_done` sweeps were already applied by the caller (zero-guess shortcut). F and W repeat
+    // residual / restriction / recursion / prolongation / post-smoothing; the second recursion (V inside F,
+    // W inside W) starts from the eps of the first one, as upstream (eps is not reset at :1126 / :1178), and
+    // uses the first recursion's test for the coarsest level (upstream's `k == DoF.size() - 2` is off by one).
+    void push_vcycle(int k, T*& cur, T*& alt, int pre_done, bool fused_top, int type = 0) {
         const gmg_params& p = st_->params;
         const int L = n_levels_;
         Level& f = lv_[k];
         Level& c = lv_[k + 1];
         push_sweeps(k, false, pre_done, p.pre_iters, cur, alt);
-        push_halo(k, HALO_A, cur);
-        {   // res = b - A x
-            Op op;
-            op.kind = OP_RESIDUAL, op.level = k, op.epi = EPI_RESIDUAL, op.plan = &f.A.plan;
-            op.args = base_args(f.A);
-            op.args.x = cur, op.args.b = f.b.ptr, op.args.out = f.r.ptr;
-            ops_.push_back(op);
-        }
-        // resRest = U^T res ; eps = 0. With a zero guess the first Jacobi sweep on the next level
-        // is eps = omega D^-1 resRest, which the restriction writes as a by-product.
         const bool next_is_coarsest = (k + 1 == L);
-        const int next_pre_done = (!next_is_coarsest && p.pre_iters >= 1) ? 1 : 0;
-        push_halo(k, HALO_R, f.r.ptr);
-        {
-            Op op;
-            op.kind = OP_RESTRICT, op.level = k, op.epi = EPI_SPMV, op.plan = &f.R.plan;
-            op.args = base_args(f.R);
-            op.args.x = f.r.ptr, op.args.out = c.b.ptr;
-            if (next_pre_done) op.args.out2 = c.x.ptr, op.args.dinv = c.dinv.ptr, op.args.omega_ptr = weight_ptr(k + 1, false, 0);
-            ops_.push_back(op);
-        }
-        if (st_->dist.sharded(k) && !st_->dist.sharded(k + 1)) {
-            // every rank restricted its own coarse rows; the next level is replicated
-            Op op;
-            op.kind = OP_ALLGATHER, op.level = k + 1, op.vec = c.b.ptr, op.vec2 = next_pre_done ? c.x.ptr : nullptr;
-            ops_.push_back(op);
-        }
+        const int halves = type == 0 ? 1 : 2;
         T* ccur = c.x.ptr;
         T* calt = c.t.ptr;
-        if (k + 1 == tail_level_) tail_begin_ = ops_.size();
-        if (next_is_coarsest) {
-            Op op;
-            op.kind = OP_COARSE, op.level = k + 1;
-            ops_.push_back(op);
-        } else {
-            if (!next_pre_done) {
+        for (int half = 0; half < halves; ++half) {
+            push_halo(k, HALO_A, cur);
+            {   // res = b - A x
                 Op op;
-                op.kind = OP_ZERO, op.level = k + 1, op.zero_ptr = c.x.ptr, op.zero_bytes = (size_t)c.n * K_ * sizeof(T);
+                op.kind = OP_RESIDUAL, op.level = k, op.epi = EPI_RESIDUAL, op.plan = &f.A.plan;
+                op.args = base_args(f.A);
+                op.args.x = cur, op.args.b = f.b.ptr, op.args.out = f.r.ptr;
                 ops_.push_back(op);
             }
-            push_vcycle(k + 1, ccur, calt, next_pre_done, false);
+            // resRest = U^T res ; eps = 0 (first recursion). With a zero guess the first Jacobi sweep on the
+            // next level is eps = omega D^-1 resRest, which the restriction writes as a by-product.
+            const bool zero_guess = half == 0;
+            const int next_pre_done = (zero_guess && !next_is_coarsest && p.pre_iters >= 1) ? 1 : 0;
+            push_halo(k, HALO_R, f.r.ptr);
+            {
+                Op op;
+                op.kind = OP_RESTRICT, op.level = k, op.epi = EPI_SPMV, op.plan = &f.R.plan;
+                op.args = base_args(f.R);
+                op.args.x = f.r.ptr, op.args.out = c.b.ptr;
+                if (next_pre_done) op.args.out2 = c.x.ptr, op.args.dinv = c.dinv.ptr, op.args.omega_ptr = weight_ptr(k + 1, false, 0);
+                ops_.push_back(op);
+            }
+            if (st_->dist.sharded(k) && !st_->dist.sharded(k + 1)) {
+                // every rank restricted its own coarse rows; the next level is replicated
+                Op op;
+                op.kind = OP_ALLGATHER, op.level = k + 1, op.vec = c.b.ptr, op.vec2 = next_pre_done ? c.x.ptr : nullptr;
+                ops_.push_back(op);
+            }
+            if (k + 1 == tail_level_) tail_begin_ = ops_.size();
+            if (next_is_coarsest) {
+                Op op;
+                op.kind = OP_COARSE, op.level = k + 1;
+                ops_.push_back(op);
+            } else {
+                if (zero_guess && !next_pre_done) {
+                    Op op;
+                    op.kind = OP_ZERO, op.level = k + 1, op.zero_ptr = ccur, op.zero_bytes = (size_t)c.n * K_ * sizeof(T);
+                    ops_.push_back(op);
+                }
+                push_vcycle(k + 1, ccur, calt, next_pre_done, false, half == 0 ? type : (type == 1 ? 0 : 2));
+            }
+            if (k + 1 == tail_level_) tail_end_ = ops_.size();
+            push_halo(k, HALO_P, ccur);
+            {   // x = x + U eps. On level 0 an odd sweep count is evened out by writing the last prolongation
+                // to the other buffer, so a cycle always ends in the buffer it started from (graph replay).
+                Op op;
+                op.kind = OP_PROLONG, op.level = k, op.epi = EPI_ADD, op.plan = &f.P.plan;
+                op.args = base_args(f.P);
+                op.args.x = ccur, op.args.xin = cur;
+                // swaps of this level: (pre - pre_done) + halves * post sweeps [+ 1 if the prolongation flips].
+                // plain cycle: end where it started (even); fused top level: start in t, end in x (odd)
+                const int sweeps_here = p.pre_iters - pre_done + halves * p.post_iters;
+                const bool flip = (k == 0) && half == halves - 1 && (fused_top ? sweeps_here % 2 == 0 : sweeps_here % 2 != 0);
+                op.args.out = flip ? alt : cur;
+                ops_.push_back(op);
+                if (flip) std::swap(cur, alt);
+            }
+            push_sweeps(k, true, 0, p.post_iters, cur, alt);
         }
-        if (k + 1 == tail_level_) tail_end_ = ops_.size();
-        push_halo(k, HALO_P, ccur);
-        {   // x = x + U eps. On level 0 an odd sweep count is evened out by writing to the other
-            // buffer, so a cycle always ends in the buffer it started from (graph replay).
-            Op op;
-            op.kind = OP_PROLONG, op.level = k, op.epi = EPI_ADD, op.plan = &f.P.plan;
-            op.args = base_args(f.P);
-            op.args.x = ccur, op.args.xin = cur;
-            // swaps of this level: (pre - pre_done) + post sweeps [+ 1 if the prolongation flips].
-            // plain cycle: end where it started (even); fused top level: start in t, end in x (odd)
-            const int sweeps_here = p.pre_iters - pre_done + p.post_iters;
-            const bool flip = (k == 0) && (fused_top ? sweeps_here % 2 == 0 : sweeps_here % 2 != 0);
-            op.args.out = flip ? alt : cur;
-            ops_.push_back(op);
-            if (flip) std::swap(cur, alt);
-        }
-        push_sweeps(k, true, 0, p.post_iters, cur, alt);
     }
 
     void build_cycle() {
@@ -1179,7 +1188,7 @@ private:
         // levels small enough to live in L2 and be launch-latency bound run as one persistent
         // kernel (tail_kernel.cuh); never the finest level, whose streaming kernels are better
         tail_level_ = -1, tail_begin_ = tail_end_ = 0;
-        for (int k = 1; k <= n_levels_ && st_->tail_rows > 0 && st_->dist.world <= 1; ++k)
+        for (int k = 1; k <= n_levels_ && st_->tail_rows > 0 && st_->dist.world <= 1 && p.cycle_type == 0; ++k)
             if (lv_[k].n <= st_->tail_rows) {
                 tail_level_ = k;
                 break;
@@ -1197,12 +1206,12 @@ private:
             Op z;
             z.kind = OP_ZERO, z.level = 0, z.zero_ptr = cur, z.zero_bytes = (size_t)lv_[0].n * K_ * sizeof(T);
             ops_.push_back(z);
-            push_vcycle(0, cur, alt, 0, false);
+            push_vcycle(0, cur, alt, 0, false, p.cycle_type);
             Op rf;  // x += e, new defect, stopping test
             rf.kind = OP_REFINE, rf.level = 0, rf.vec = cur;
             ops_.push_back(rf);
         } else if (!fused) {
-            push_vcycle(0, cur, alt, 0, false);
+            push_vcycle(0, cur, alt, 0, false, p.cycle_type);
         } else {
             // prologue (once per solve): sweep 0 of the first cycle, x (cur) -> alt
             push_sweeps(0, false, 0, 1, cur, alt);
@@ -1210,7 +1219,7 @@ private:
             ops_.clear();
             // every cycle starts from the swept iterate in `cur` (= lv_[0].t) and must end with the
             // final iterate in lv_[0].x so that the speculative sweep lands in lv_[0].t again
-            push_vcycle(0, cur, alt, 1, true);
+            push_vcycle(0, cur, alt, 1, true, p.cycle_type);
         }
         if (tail_level_ > 0 && tail_end_ > tail_begin_) collapse_tail();
         x_final_ = cur;

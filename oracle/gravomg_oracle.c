@@ -70,6 +70,7 @@ typedef struct orc_solver {
     int have_setup;
     /* parameters the binding sets (core.cpp:52-57) */
     int pre_iters, post_iters, max_iter, criterion, smoother; /* smoother 0 = GS (reference), 1 = damped Jacobi */
+    int cycle_type; /* 0 V, 1 F, 2 W (core.cpp:52; multigrid_solver.cpp:1420-1439) */
     double tol, omega;
     double w_pre[ORC_MAX_LEVELS][ORC_MAX_SWEEPS], w_post[ORC_MAX_LEVELS][ORC_MAX_SWEEPS]; /* Jacobi damping per level and sweep */
     /* outputs */
@@ -553,8 +554,13 @@ static void smooth(const orc_solver* s, const csc_t* A, const double* b, double*
     }
 }
 
-/* multiGridVCycleGS (multigrid_solver.cpp:1059-1088). */
-static void vcycle(const orc_solver* s, const csc_t* A, const double* b, double* x, int K, int k) {
+/* type 0: multiGridVCycleGS (multigrid_solver.cpp:1059-1088); 1: multiGridFCycleGS (:1091-1140); 2: multiGridWCycleGS
+ * (:1143-1192). The F- and W-cycles repeat residual / restriction / recursion / prolongation / post-smoothing; the
+ * second recursion (a V-cycle for F, a W-cycle for W) starts from the eps of the first one (eps is not reset at :1126 /
+ * :1178). Upstream tests `k == DoF.size() - 2` for the coarsest level there, which is off by one whenever the hierarchy
+ * stopped at lowBound (DoF keeps the discarded level, :129,156-159) and then indexes past U; restated with the test of
+ * the first recursion (`k == U.size() - 1`), the evident intent. */
+static void cycle(const orc_solver* s, const csc_t* A, const double* b, double* x, int K, int k, int type) {
     const int n = A->cols;
     if (s->n_levels == 0) { /* undefined upstream (U[0] out of range); whole system to the direct solver */
         double* work = (double*)malloc(sizeof(double) * (size_t)n);
@@ -566,21 +572,30 @@ static void vcycle(const orc_solver* s, const csc_t* A, const double* b, double*
     const int nc = U->cols;
     smooth(s, A, b, x, K, s->pre_iters, s->w_pre[k]);
     double* res = (double*)malloc(sizeof(double) * (size_t)n * K);
-    orc_residual(n, A->colptr, A->rowidx, A->vals, b, x, res, K);
     double* rest = (double*)malloc(sizeof(double) * (size_t)nc * K);
-    orc_restrict(n, nc, U->colptr, U->rowidx, U->vals, res, rest, K);
     double* eps = (double*)calloc((size_t)nc * K, sizeof(double));
-    if (k == s->n_levels - 1) {
-        double* work = (double*)malloc(sizeof(double) * (size_t)nc);
-        for (int c = 0; c < K; ++c) ldl_solve(&s->coarse, rest + (size_t)c * nc, eps + (size_t)c * nc, work);
-        free(work);
-    } else {
-        vcycle(s, &s->Abar[k + 1], rest, eps, K, k + 1);
+    for (int half = 0; half < (type == 0 ? 1 : 2); ++half) {
+        orc_residual(n, A->colptr, A->rowidx, A->vals, b, x, res, K);
+        orc_restrict(n, nc, U->colptr, U->rowidx, U->vals, res, rest, K);
+        if (k == s->n_levels - 1) {
+            double* work = (double*)malloc(sizeof(double) * (size_t)nc);
+            for (int c = 0; c < K; ++c) ldl_solve(&s->coarse, rest + (size_t)c * nc, eps + (size_t)c * nc, work);
+            free(work);
+        } else {
+            /* first recursion: the same cycle type; second: V inside an F-cycle, W inside a W-cycle */
+            cycle(s, &s->Abar[k + 1], rest, eps, K, k + 1, half == 0 ? type : (type == 1 ? 0 : 2));
+        }
+        orc_prolong_add(n, nc, U->colptr, U->rowidx, U->vals, eps, x, K);
+        smooth(s, A, b, x, K, s->post_iters, s->w_post[k]);
     }
-    orc_prolong_add(n, nc, U->colptr, U->rowidx, U->vals, eps, x, K);
-    smooth(s, A, b, x, K, s->post_iters, s->w_post[k]);
     free(res), free(rest), free(eps);
 }
+
+static void vcycle(const orc_solver* s, const csc_t* A, const double* b, double* x, int K, int k) {
+    cycle(s, A, b, x, K, k, s->cycle_type);
+}
+
+void orc_set_cycle_type(orc_solver* s, int cycle_type) { s->cycle_type = cycle_type; }
 
 /* One V-cycle from level 0 after orc_setup (for cycle-level parity checks). */
 int orc_vcycle(orc_solver* s, const int* cp, const int* ri, const double* v, const double* b, double* x, int K) {

@@ -47,6 +47,7 @@ def _load():
         "orc_destroy": (None, [C.c_void_p]),
         "orc_add_prolongation": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _i32p, _i32p, _f64p]),
         "orc_set_params": (None, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]),
+        "orc_set_cycle_type": (None, [C.c_void_p, C.c_int]),
         "orc_setup": (C.c_int, [C.c_void_p, _i32p, _i32p, _f64p]),
         "orc_vcycle": (C.c_int, [C.c_void_p, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_int]),
         "orc_coarse_solve": (C.c_int, [C.c_void_p, _f64p, _f64p, C.c_int]),
@@ -181,7 +182,7 @@ class OracleSolver:
     ``'jacobi'`` is the op-for-op counterpart of the device path."""
 
     def __init__(self, mass, U, pre_iters=2, post_iters=2, max_iter=100, stopping_criteria=2, tolerance=1e-4,
-                 smoother="gs", omega=2.0 / 3.0, weights=None):
+                 smoother="gs", omega=2.0 / 3.0, weights=None, cycle_type=0):
         m = mass.diagonal() if sp.issparse(mass) else np.asarray(mass)
         self.mass = np.ascontiguousarray(m, dtype=np.float64)
         self.n = self.mass.shape[0]
@@ -194,6 +195,7 @@ class OracleSolver:
         self.max_iter = int(max_iter)
         lib().orc_set_params(self._h, int(pre_iters), int(post_iters), int(max_iter), int(stopping_criteria),
                              float(tolerance), {"gs": 0, "jacobi": 1}[smoother], float(omega))
+        lib().orc_set_cycle_type(self._h, int(cycle_type))
         self.convergence = []
         if weights is not None:  # {level: (pre_omegas, post_omegas)}
             for level, (pre, post) in dict(weights).items():

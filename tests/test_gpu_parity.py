@@ -269,6 +269,35 @@ def test_p2_one_vcycle_matches_the_oracle_jacobi_cycle(ico_small, K, smoother):
     assert solver.solver_timing["residue"] == pytest.approx(o.solver_timing["residue"], rel=1e-9)
 
 
+@pytest.mark.parametrize("K", [1, 3])
+@pytest.mark.parametrize("cycle_type", [1, 2])
+def test_p2_f_and_w_cycles_match_the_oracle(ico_small, cycle_type, K):
+    """cycle_type 1 / 2 (multigrid_solver.cpp:1091-1192, with the coarsest-level test fixed): one device
+    cycle and a whole solve against the oracle running the same cycle with the device's sweeps."""
+    p = ico_small
+    lhs = (p.M + 1e-3 * p.S).tocsr()
+    rhs = (p.M @ p.V)[:, :K]
+    one = p.new_solver(max_iter=1, cycle_type=cycle_type)
+    x = one.solve(lhs, rhs)
+    o = _jacobi_oracle(p, one, max_iter=1, cycle_type=cycle_type)
+    want = o.solve(lhs, rhs)
+    assert np.linalg.norm(x - want) <= 1e-12 * np.linalg.norm(want)
+    v = p.new_solver(max_iter=1)
+    assert np.linalg.norm(x - v.solve(lhs, rhs)) > 1e-9 * np.linalg.norm(want)  # not a V-cycle
+    full = p.new_solver(tolerance=1e-8, cycle_type=cycle_type)
+    xf = full.solve(lhs, rhs)
+    of = _jacobi_oracle(p, full, tolerance=1e-8, cycle_type=cycle_type)
+    of.solve(lhs, rhs)
+    vf = p.new_solver(tolerance=1e-8)
+    vf.solve(lhs, rhs)
+    assert full.solver_timing["iterations"] == of.solver_timing["iterations"] <= vf.solver_timing["iterations"]
+    assert oracle.residual_check(lhs, rhs, xf, 2, p.m) <= 1e-8
+    # launch modes agree
+    host = p.new_solver(tolerance=1e-8, cycle_type=cycle_type)
+    host.solver.set_option("loop_mode", 0)
+    np.testing.assert_array_equal(host.solve(lhs, rhs), xf)
+
+
 def test_p2_one_vcycle_poisson(ico_small):
     p = ico_small
     solver = p.new_solver(max_iter=1)

@@ -164,6 +164,42 @@ def test_vcycle_matches_a_numpy_vcycle(ico_small):
     check(p.lhs, p.rhs, lambda A, got, want: np.linalg.norm(A @ (got - want)) <= 2 * eps * abs(A).sum(0).max() * np.linalg.norm(want))
 
 
+@pytest.mark.parametrize("cycle_type", [1, 2])
+def test_f_and_w_cycles_match_a_numpy_restatement(ico_small, cycle_type):
+    """multigrid_solver.cpp:1091-1140 (F) and 1143-1192 (W): the second recursion starts from the eps of
+    the first one; F recurses with F then V, W with W twice. Three levels, so the recursion pattern shows."""
+    p = ico_small
+    lhs = (p.M + 1e-3 * p.S).tocsr()
+    rhs = p.M @ p.V
+    o = oracle.OracleSolver(p.M, p.U, smoother="gs", cycle_type=cycle_type)
+    o.setup(lhs)
+    A = [lhs] + [a.tocsr() for a in o.level_matrices()]
+    coarse = sla.splu(sp.csc_matrix(A[-1]))
+
+    def cycle(k, b, x, kind):
+        x = oracle.gauss_seidel(A[k], b, x, 2)
+        e = None
+        for half in range(1 if kind == 0 else 2):
+            rc = p.U[k].T @ (b - A[k] @ x)
+            if k == len(p.U) - 1:
+                e = coarse.solve(rc)
+            else:
+                e = cycle(k + 1, rc, np.zeros_like(rc) if e is None else e, kind if half == 0 else (0 if kind == 1 else 2))
+            x = oracle.gauss_seidel(A[k], b, x + p.U[k] @ e, 2)
+        return x
+
+    want = cycle(0, rhs, rhs.copy(), cycle_type)
+    got = o.vcycle(lhs, rhs, rhs)
+    assert np.linalg.norm(got - want) <= 1e-12 * np.linalg.norm(want)
+    v = oracle.OracleSolver(p.M, p.U, smoother="gs")
+    v.setup(lhs)
+    assert np.linalg.norm(got - v.vcycle(lhs, rhs, rhs)) > 1e-9 * np.linalg.norm(want)  # not a V-cycle
+    # and the loop converges in no more cycles than with V-cycles
+    o.solve(lhs, rhs)
+    v.solve(lhs, rhs)
+    assert o.solver_timing["iterations"] <= v.solver_timing["iterations"] and o.solver_timing["residue"] <= 1e-4
+
+
 @pytest.mark.parametrize("smoother", ["gs", "jacobi"])
 def test_config1_poisson_10k_converges_to_the_direct_solution(ico10k, smoother):
     """BASELINE config 1: 10 242-vertex icosphere Poisson solve on the CPU path."""
