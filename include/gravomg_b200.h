@@ -36,7 +36,7 @@ enum { GMG_DTYPE_F64 = 0, GMG_DTYPE_F32 = 1 };
 typedef struct gmg_params {
     double ratio;               /* 8.0   */
     int32_t low_bound;          /* 1000  */
-    int32_t cycle_type;         /* 0 = V-cycle (only 0 is on the accelerated path) */
+    int32_t cycle_type;         /* 0 = V-cycle, 1 = F-cycle, 2 = W-cycle (multigrid_solver.cpp:1059-1192) */
     double tolerance;           /* 1e-4  */
     int32_t stopping_criteria;  /* 2 = M-norm relative residual (multigrid_solver.cpp:1228-1277) */
     int32_t pre_iters;          /* 2 */
