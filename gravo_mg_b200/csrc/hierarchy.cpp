@@ -5,9 +5,18 @@
 #include <cmath>
 #include <cstdio>
 #include <limits>
+#include <cstdlib>
 #include <queue>
+#include <thread>
 
 namespace gmg {
+
+// Worker threads of the per-point selection: GMG_HIERARCHY_THREADS, else the hardware concurrency (at most 8).
+static int hierarchy_threads() {
+    if (const char* e = std::getenv("GMG_HIERARCHY_THREADS")) return std::max(1, std::atoi(e));
+    return (int)std::max(1u, std::thread::hardware_concurrency());
+}
+
 namespace {
 
 struct Vec3 {
@@ -355,24 +364,24 @@ void build_hierarchy(const double* pos_in, int64_t n, const int* neigh_in, int k
         rows.vals.reserve(3 * nf);
         std::vector<int> missing;
         if (opt.debug) missing.assign(nf, 0);
-        std::vector<EdgeFlag> flags;
-        std::vector<std::pair<double, int>> by_distance;
-        for (int64_t i = 0; i < nf; ++i) {
+        // Every fine point is independent of the others (multigrid_solver.cpp:293-453): the selection runs on
+        // worker threads over contiguous chunks into per-point slots, the rows are assembled in order afterwards.
+        std::vector<int> sel_ids(3 * (size_t)nf);
+        std::vector<double> sel_w(3 * (size_t)nf);
+        std::vector<unsigned char> sel_count((size_t)nf);
+        auto select = [&](int64_t i, int* ids, double* w, std::vector<EdgeFlag>& flags,
+                          std::vector<std::pair<double, int>>& by_distance) -> int {
             const Vec3 p = level.at(i);
             const int c = nearest[i];
             const Vec3 pc = coarse.at(c);
-            int ids[3];
-            double w[3];
             if (opt.nested && picked[c] == i) {
                 ids[0] = c, w[0] = 1.0;
-                rows.push_row(ids, w, 1);
-                continue;
+                return 1;
             }
             const auto& a = adj[c];
             if (a.empty()) {
                 ids[0] = c, w[0] = 1.0;
-                rows.push_row(ids, w, 1);
-                continue;
+                return 1;
             }
             if (a.size() == 1) {
                 ids[0] = c, ids[1] = a[0];
@@ -384,8 +393,7 @@ void build_hierarchy(const double* pos_in, int64_t n, const int* neigh_in, int k
                 } else {
                     inverse_distance_weights(coarse, p, ids, 2, w);
                 }
-                rows.push_row(ids, w, 2);
-                continue;
+                return 2;
             }
             // first incident triangle (creation order, rotated so c leads) containing the projection
             flags.clear();
@@ -411,8 +419,8 @@ void build_hierarchy(const double* pos_in, int64_t n, const int* neigh_in, int k
                     w[0] = w[1] = w[2] = 1.0 / 3.0;
                 else
                     inverse_distance_weights(coarse, p, hit, 3, w);
-                rows.push_row(hit, w, 3);
-                continue;
+                std::copy(hit, hit + 3, ids);
+                return 3;
             }
             if (opt.debug) missing[i] = 1;
             // else the lowest-numbered neighbour whose edge is still flagged "inside"
@@ -429,8 +437,7 @@ void build_hierarchy(const double* pos_in, int64_t n, const int* neigh_in, int k
                 } else {
                     inverse_distance_weights(coarse, p, ids, 2, w);
                 }
-                rows.push_row(ids, w, 2);
-                continue;
+                return 2;
             }
             // else own cluster plus the two closest stored coarse neighbours, inverse-distance weighted
             by_distance.clear();
@@ -445,8 +452,23 @@ void build_hierarchy(const double* pos_in, int64_t n, const int* neigh_in, int k
             ids[0] = c;
             for (size_t j = 0; j < by_distance.size() && count < 3; ++j) ids[count++] = by_distance[j].second;
             inverse_distance_weights(coarse, p, ids, count, w);
-            rows.push_row(ids, w, count);
+            return count;
+        };
+        {
+            const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)hierarchy_threads(), 8, nf / 4096 + 1}));
+            auto work = [&](int t) {
+                std::vector<EdgeFlag> flags;
+                std::vector<std::pair<double, int>> by_distance;
+                const int64_t lo = nf * t / n_threads, hi = nf * (t + 1) / n_threads;
+                for (int64_t i = lo; i < hi; ++i)
+                    sel_count[i] = (unsigned char)select(i, &sel_ids[3 * i], &sel_w[3 * i], flags, by_distance);
+            };
+            std::vector<std::thread> pool;
+            for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+            work(0);
+            for (auto& th : pool) th.join();
         }
+        for (int64_t i = 0; i < nf; ++i) rows.push_row(&sel_ids[3 * i], &sel_w[3 * i], sel_count[i]);
         if (opt.debug) out.no_tri_found.push_back(std::move(missing));
         tm["triangle_selection"] += t_sel.ms();
 
