@@ -138,6 +138,11 @@ int gmg_set_option(gmg_handle h, const char* key, double value) {
         SolverState& s = h->s;
         const std::string k(key);
         bool cycle = false, hierarchy = false;
+        // a rejected value must not stay behind (the cached launch list would run with it): keep the
+        // validated fields and put them back if a check below throws
+        const gmg_params saved_params = s.params;
+        const int saved_xfer = s.xfer_threads, saved_lanes = s.staged_lanes, saved_lanes_r = s.staged_lanes_r;
+        try {
         if (k == "tolerance") s.params.tolerance = value;
         else if (k == "max_iter") s.params.max_iter = (int)value;
         else if (k == "stopping_criteria") s.params.stopping_criteria = (int)value, cycle = true;
@@ -168,12 +173,22 @@ int gmg_set_option(gmg_handle h, const char* key, double value) {
         else if (k == "dist_skip_exchange") s.dist_skip_exchange = value != 0.0, cycle = true;
         else if (k == "spgemm_plan") s.spgemm_plan = value != 0.0, hierarchy = true;
         else if (k == "coarse_dataflow") s.coarse_dataflow = value != 0.0, cycle = true;
+        else if (k == "diff_form") s.diff_form = value != 0.0, hierarchy = true;
         else throw std::invalid_argument("unknown option: " + k);
         require(s.params.pre_iters >= 0 && s.params.post_iters >= 0 && s.params.pre_iters <= 16 && s.params.post_iters <= 16, "sweep counts must be 0..16");
         require(s.params.smoother == GMG_SMOOTHER_JACOBI || s.params.smoother == GMG_SMOOTHER_CHEBYSHEV, "unknown smoother");
         require(s.params.cheb_alpha > 1.0, "cheb_alpha must be > 1");
         require(s.xfer_threads >= -1 && s.xfer_threads <= 64, "xfer_threads must be -1 (auto), 0 (off) or 1..64");
         require(s.staged_lanes == 0 || s.staged_lanes == 1 || s.staged_lanes == 2 || s.staged_lanes == 4 || s.staged_lanes == 8, "lanes must be 0, 1, 2, 4 or 8");
+        require(s.staged_lanes_r == 0 || s.staged_lanes_r == 1 || s.staged_lanes_r == 2 || s.staged_lanes_r == 4 || s.staged_lanes_r == 8, "lanes_r must be 0, 1, 2, 4 or 8");
+        require(s.params.max_iter >= 1, "max_iter must be >= 1");
+        require(s.params.cycle_type >= 0 && s.params.cycle_type <= 2, "cycle_type must be 0 (V), 1 (F) or 2 (W)");
+        require(s.params.stopping_criteria >= 0 && s.params.stopping_criteria <= 3, "stopping_criteria must be 0..3");
+        } catch (...) {
+            s.params = saved_params;
+            s.xfer_threads = saved_xfer, s.staged_lanes = saved_lanes, s.staged_lanes_r = saved_lanes_r;
+            throw;
+        }
         if (s.engine && hierarchy) s.engine->invalidate_hierarchy();
         if (s.engine && cycle) s.engine->invalidate_cycle();
     });
@@ -215,6 +230,7 @@ int gmg_get_option(gmg_handle h, const char* key, double* value) {
         else if (k == "dist_skip_exchange") *value = s.dist_skip_exchange;
         else if (k == "spgemm_plan") *value = s.spgemm_plan;
         else if (k == "coarse_dataflow") *value = s.coarse_dataflow;
+        else if (k == "diff_form") *value = s.diff_form;
         else throw std::invalid_argument("unknown option: " + k);
     });
 }

@@ -40,6 +40,8 @@ struct DevMat {
     DeviceBuffer<int4> tiles;
     DeviceBuffer<double> v64;
     DeviceBuffer<float> v32;
+    DeviceBuffer<double> vd;  // finest level, option diff_form: v64 with the row sum in place of the diagonal (SpmvArgs::diff)
+    bool diff = false;
     SpmvPlan plan;
 
     const T* vals() const;
@@ -133,8 +135,8 @@ public:
         GMG_CUDA(cudaStreamCreateWithFlags(&stream2_, cudaStreamNonBlocking));
         GMG_CUDA(cudaEventCreateWithFlags(&rhs_ready_, cudaEventDisableTiming));
         for (auto& e : ev_) GMG_CUDA(cudaEventCreate(&e));
-        ctl_.ensure(2);
-        GMG_CUDA(cudaMemsetAsync(ctl_.ptr, 0, 2 * sizeof(CycleControl), stream_));
+        ctl_.ensure(3);
+        GMG_CUDA(cudaMemsetAsync(ctl_.ptr, 0, 3 * sizeof(CycleControl), stream_));
         partials_.ensure(kNormChunkStride * kMaxNormChunks);
         rho_.ensure(kMaxLevels);
         tail_bar_.ensure(4);
@@ -384,6 +386,13 @@ public:
         SpmvArgs<double> a;
         a.n_rows = (int)n, a.ld = K;
         a.rowptr = q_indptr_.ptr, a.colidx = q_indices_.ptr, a.vals = q_vals_.ptr;
+        if (st_->diff_form) {
+            // the same cancellation-free row product the cycle's stopping test uses (scratch: loop-state slot 2)
+            q_vd_.ensure((size_t)nnz, 8), q_dinv_.ensure((size_t)n), q_rho_.ensure(1);
+            launch_extract_dinv<double>((int)n, q_indptr_.ptr, q_indices_.ptr, q_vals_.ptr, q_dinv_.ptr, q_rho_.ptr, ctl_.ptr + 2,
+                                        stream_, q_vd_.ptr);
+            a.vals = q_vd_.ptr, a.diff = 1;
+        }
         a.weight = type == 2 ? mass_.ptr : type == 1 ? minv_.ptr : nullptr;
         NormChunks chunks;
         for (int k0 = 0; k0 < K; k0 += kMaxRhsTile) {
@@ -410,7 +419,7 @@ public:
         GMG_CUDA(cudaMemsetAsync(rho_.ptr, 0, kMaxLevels * sizeof(double), stream_));
         if (L > 0) {
             launch_extract_dinv<T>(lv_[0].n, lv_[0].A.indptr.ptr, lv_[0].A.indices.ptr, lv_[0].A.v64.ptr, lv_[0].dinv.ptr,
-                                   rho_.ptr, ctl_.ptr, stream_);
+                                   rho_.ptr, ctl_.ptr, stream_, lv_[0].A.diff ? lv_[0].A.vd.ptr : nullptr);
             ++launches;
         }
         lv_[0].A.refresh_cast(stream_);
@@ -766,6 +775,11 @@ private:
         }
         for (int k = 0; k <= n_levels_; ++k) {
             lv_[k].A.upload_pattern(st_->a_pat[k], stream_);
+            if (k == 0 && n_levels_ > 0 && st_->diff_form) {
+                lv_[0].A.vd.ensure(lv_[0].A.nnz, 8);
+                GMG_CUDA(cudaMemsetAsync(lv_[0].A.vd.ptr, 0, (lv_[0].A.nnz + 8) * sizeof(double), stream_));
+                lv_[0].A.diff = true;
+            }
             if (k > 0) lv_[k].A.make_rowidx(stream_);
             range(k, d.sharded(k), b, e);
             if (d.sharded(k)) {  // sweeps / residual / norm: write x_k (gathered through A_k, or U_{k-1}) or r_k (through R_k)
@@ -1061,6 +1075,7 @@ private:
         a.n_rows = m.rows;
         a.ld = K_;
         a.rowptr = m.indptr.ptr, a.colidx = m.indices.ptr, a.vals = m.vals();
+        if (m.diff && sizeof(T) == 8) a.vals = reinterpret_cast<const T*>(m.vd.ptr), a.diff = 1;
         a.l2_hint = st_->l2_hints ? m.l2_hint : 0;
         a.omega = (T)st_->params.omega;
         a.ctl = ctl_.ptr;
@@ -1429,6 +1444,7 @@ private:
                 SpmvArgs<double> a;
                 a.n_rows = lv_[0].n, a.ld = K_;
                 a.rowptr = lv_[0].A.indptr.ptr, a.colidx = lv_[0].A.indices.ptr, a.vals = lv_[0].A.v64.ptr;
+                if (lv_[0].A.diff) a.vals = lv_[0].A.vd.ptr, a.diff = 1;
                 a.weight = p.stopping_criteria == 2 ? mass_.ptr : p.stopping_criteria == 1 ? minv_.ptr : nullptr;
                 a.ctl = ctl_.ptr;
                 const bool test = op.level >= 0;
@@ -1639,7 +1655,7 @@ private:
     DeviceBuffer<unsigned long long> trace_buf_;
     DeviceBuffer<T> weights_;
     DeviceBuffer<int> q_indptr_, q_indices_;
-    DeviceBuffer<double> q_vals_, q_b_, q_x_;
+    DeviceBuffer<double> q_vals_, q_b_, q_x_, q_vd_, q_dinv_, q_rho_;
     std::vector<DevHalo> halo_[3];
     size_t max_halo_ = 0;
     DeviceBuffer<T> halo_send_, halo_recv_;

@@ -68,6 +68,8 @@ struct SolverState {
     bool fuse_norm = true;           // stopping test fused with the next cycle's first sweep
     bool use_pdl = true;             // programmatic dependent launch of the row-product kernels
     bool coarse_dataflow = true;     // coarse factor as one dataflow kernel (dense_factor.cuh) / one kernel per phase
+    bool diff_form = true;           // finest level: cancellation-free row product sum_{j != i} A_ij (x_j - x_i) + s_i x_i
+                                     // (sparse_kernels.cuh, SpmvArgs::diff); false: plain sum_j A_ij x_j
     bool spgemm_plan = true;         // Galerkin products from index-pair lists built once per pattern
     long long spgemm_plan_max_pairs = 1500000000ll;  // 12 GB of pairs; beyond it levels fall back to the searching kernel
     int xfer_threads = -1;           // host threads staging caller buffers through pinned chunks (host_xfer.h);

@@ -94,15 +94,32 @@ template <typename T>
 __global__ void __launch_bounds__(256) extract_dinv_kernel(int n, const int* __restrict__ rowptr,
                                                           const int* __restrict__ colidx,
                                                           const double* __restrict__ vals, T* __restrict__ dinv,
-                                                          double* __restrict__ rho, CycleControl* ctl) {
+                                                          double* __restrict__ rho, CycleControl* ctl,
+                                                          double* __restrict__ vals_diff) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double bound = 0.0;
     if (i < n) {
         double d = 0.0, absum = 0.0;
+        double s = 0.0, e = 0.0;  // row sum by an error-free TwoSum chain: s the running sum, e its rounding errors
         for (int p = rowptr[i]; p < rowptr[i + 1]; ++p) {
             const double v = vals[p];
             if (colidx[p] == i) d += v;
             absum += fabs(v);
+            const double t = s + v;
+            const double bp = t - s;
+            e += (s - (t - bp)) + (v - bp);
+            s = t;
+        }
+        if (vals_diff) {
+            // operator of the cancellation-free row product: off-diagonal entries as they are, the row
+            // sum in place of the (first stored) diagonal entry
+            const double rowsum = s + e;
+            bool seen = false;
+            for (int p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+                const bool diag = colidx[p] == i;
+                vals_diff[p] = diag ? (seen ? 0.0 : rowsum) : vals[p];
+                seen = seen || diag;
+            }
         }
         if (!(d > 0.0) || d > 1.7976931348623157e308) {
             atomicOr(&ctl->error, 1);
@@ -438,13 +455,13 @@ void launch_cycle_begin(CycleControl* ctl, int max_iter, int criterion, double t
 
 template <typename T>
 void launch_extract_dinv(int n, const int* rowptr, const int* colidx, const double* vals, T* dinv, double* rho,
-                         CycleControl* ctl, cudaStream_t stream) {
+                         CycleControl* ctl, cudaStream_t stream, double* vals_diff) {
     if (n <= 0) return;
-    extract_dinv_kernel<T><<<(n + 255) / 256, 256, 0, stream>>>(n, rowptr, colidx, vals, dinv, rho, ctl);
+    extract_dinv_kernel<T><<<(n + 255) / 256, 256, 0, stream>>>(n, rowptr, colidx, vals, dinv, rho, ctl, vals_diff);
     GMG_CUDA(cudaGetLastError());
 }
-template void launch_extract_dinv<double>(int, const int*, const int*, const double*, double*, double*, CycleControl*, cudaStream_t);
-template void launch_extract_dinv<float>(int, const int*, const int*, const double*, float*, double*, CycleControl*, cudaStream_t);
+template void launch_extract_dinv<double>(int, const int*, const int*, const double*, double*, double*, CycleControl*, cudaStream_t, double*);
+template void launch_extract_dinv<float>(int, const int*, const int*, const double*, float*, double*, CycleControl*, cudaStream_t, double*);
 
 template <typename T>
 void launch_smoother_weights(const double* rho, int n_levels, int pre, int post, int smoother, double omega, double alpha,

@@ -131,6 +131,13 @@ struct SpmvArgs {
     int l2_hint = 0;                   // staged: L2 eviction priority of the operator slabs (0 none, 1 keep, 2 stream)
     int n_early = 0;                   // staged: tiles [0, n_early) hold every row that is pushed or gathers halo
                                        // entries; the exchange is signalled once they are done (rest overlaps)
+    // cancellation-free row product (square operators): `vals` then holds the ROW SUM s_i in place of the
+    // diagonal entry (extract_dinv_kernel) and the kernels evaluate
+    //     acc_i = sum_{j != i} A_ij (x_j - x_i) + s_i x_i        (= sum_j A_ij x_j in exact arithmetic).
+    // A Poisson system tau M + S has row sums ~1e-12 next to entries ~1 and an iterate that carries a
+    // constant ~1/(tau sqrt N): in the plain form the products of that constant cancel and leave a
+    // rounding floor ~1e-6 in the relative residual at >= 4 M vertices (tools/stall_study.py).
+    int diff = 0;
 };
 
 #ifdef __CUDACC__
@@ -396,16 +403,21 @@ __global__ void __launch_bounds__(TPB + 32) spmv_staged_kernel(const SpmvArgs<T>
                 pe = rp[o + 1] - d.z;
                 if (lane == 0) load_row_operands<T, K, EPI>(a, row, ops);
             }
-            T acc[K];
+            T acc[K], xi[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] = T(0);
+            for (int k = 0; k < K; ++k) acc[k] = T(0), xi[k] = T(0);
+            if (a.diff && active) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) xi[k] = __ldg(a.x + (size_t)row * a.ld + k);
+            }
 #pragma unroll 8
             for (int p = ps + lane; p < pe; p += LANES) {
                 const int c = sc[p];
                 const T v = sv[p];
                 const T* xp = a.x + (size_t)c * a.ld;
+                const bool off = a.diff && c != row;  // plain form: x_j - 0 = x_j, bit for bit
 #pragma unroll
-                for (int k = 0; k < K; ++k) acc[k] += v * __ldg(xp + k);
+                for (int k = 0; k < K; ++k) acc[k] += v * (__ldg(xp + k) - (off ? xi[k] : T(0)));
             }
             // every lane of the warp has read its part of stage s: hand it back to the producer
             __syncwarp();
@@ -451,17 +463,22 @@ __global__ void __launch_bounds__(kDirectThreads) spmv_direct_kernel(const SpmvA
     for (int first = a.row_begin + blockIdx.x * rows_per_block; first < a.n_rows; first += gridDim.x * rows_per_block) {
         const int row = first + threadIdx.x / LANES;
         const bool active = row < a.n_rows;
-        T acc[K];
+        T acc[K], xi[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = T(0);
+        for (int k = 0; k < K; ++k) acc[k] = T(0), xi[k] = T(0);
         if (active) {
+            if (a.diff) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) xi[k] = __ldg(a.x + (size_t)row * a.ld + k);
+            }
             const int pe = a.rowptr[row + 1];
             for (int p = a.rowptr[row] + lane; p < pe; p += LANES) {
                 const int c = __ldg(a.colidx + p);
                 const T v = __ldg(a.vals + p);
                 const T* xp = a.x + (size_t)c * a.ld;
+                const bool off = a.diff && c != row;
 #pragma unroll
-                for (int k = 0; k < K; ++k) acc[k] += v * __ldg(xp + k);
+                for (int k = 0; k < K; ++k) acc[k] += v * (__ldg(xp + k) - (off ? xi[k] : T(0)));
             }
         }
 #pragma unroll

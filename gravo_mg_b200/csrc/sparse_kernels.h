@@ -62,9 +62,11 @@ void launch_cycle_begin(CycleControl* ctl, int max_iter, int criterion, double t
 constexpr int kMaxSweeps = 16;        // pre / post sweeps per level the weight table holds
 
 // dinv = 1 / diag(A) and *rho = max(*rho, Gershgorin bound of D^-1 A) (zero *rho first).
+// vals_diff != nullptr: also the value array of the cancellation-free row product (SpmvArgs::diff):
+// a copy of vals with the row sum (error-free TwoSum accumulation) in place of the diagonal entry.
 template <typename T>
 void launch_extract_dinv(int n, const int* rowptr, const int* colidx, const double* vals, T* dinv, double* rho,
-                         CycleControl* ctl, cudaStream_t stream);
+                         CycleControl* ctl, cudaStream_t stream, double* vals_diff = nullptr);
 // Jacobi dampings per level and sweep from rho[level]: weights[(level * 2 + post) * kMaxSweeps + sweep].
 template <typename T>
 void launch_smoother_weights(const double* rho, int n_levels, int pre, int post, int smoother, double omega, double alpha,

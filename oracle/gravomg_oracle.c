@@ -28,6 +28,14 @@
  *                        ordering only changes rounding (the exact-arithmetic solution is the
  *                        same); the parity tests therefore compare coarse solves to 1e-9.
  *
+ *   *_diff               NOT in the reference: the device path's cancellation-free row product on the
+ *                        finest level, sum_{j != i} A_ij (x_j - x_i) + s_i x_i with s_i the row sum of
+ *                        A accumulated with an error-free TwoSum chain (orc_rowsum). Algebraically the
+ *                        same A x; on Poisson systems tau M + S the iterate carries a constant of size
+ *                        1/(tau sqrt N) whose products cancel in the plain form and leave a rounding
+ *                        floor of ~1e-6 in the relative residual at >= 4 M vertices. Only the Jacobi
+ *                        variant (the device's cycle) uses it; the Gauss-Seidel reference path does not.
+ *
  * Conventions: sparse matrices are CSC with int32 indices (what the pybind11 Eigen caster
  * hands the reference); dense blocks are column-major n x K (Eigen::MatrixXd).
  * Compile with -ffp-contract=off so a*b+c is never fused (the device kernels are compiled
@@ -71,6 +79,7 @@ typedef struct orc_solver {
     /* parameters the binding sets (core.cpp:52-57) */
     int pre_iters, post_iters, max_iter, criterion, smoother; /* smoother 0 = GS (reference), 1 = damped Jacobi */
     int cycle_type; /* 0 V, 1 F, 2 W (core.cpp:52; multigrid_solver.cpp:1420-1439) */
+    int row_product; /* Jacobi variant only: 1 = cancellation-free row product on level 0 (the device default) */
     double tol, omega;
     double w_pre[ORC_MAX_LEVELS][ORC_MAX_SWEEPS], w_post[ORC_MAX_LEVELS][ORC_MAX_SWEEPS]; /* Jacobi damping per level and sweep */
     /* outputs */
@@ -252,6 +261,76 @@ void orc_jacobi(int n, const int* cp, const int* ri, const double* v, const doub
     }
 }
 
+/* ------------------------------------------------------------------ cancellation-free row product (device path) */
+/* s_k = sum of the stored entries of column k (= row k), accumulated in stored order with Knuth's
+ * TwoSum: `s` is the running floating-point sum, `e` collects the rounding error of every addition,
+ * the result is s + e. Exact to ~eps^2 sum|A_kj|: the row sums of tau M + S are ~1e-12 next to entries ~1. */
+void orc_rowsum(int n, const int* cp, const double* v, double* out) {
+    for (int k = 0; k < n; ++k) {
+        double s = 0.0, e = 0.0;
+        for (int p = cp[k]; p < cp[k + 1]; ++p) {
+            const double a = v[p];
+            const double t = s + a;
+            const double bp = t - s;
+            const double err = (s - (t - bp)) + (a - bp);
+            s = t;
+            e += err;
+        }
+        out[k] = s + e;
+    }
+}
+
+/* (A x)_k = sum_p term_p in stored order: off-diagonal entries contribute A_kj (x_j - x_k), the first
+ * stored diagonal entry contributes s_k x_k, further (duplicate) diagonal entries nothing. */
+static double row_product_diff(const int* cp, const int* ri, const double* v, const double* rowsum, const double* xc, int k) {
+    double acc = 0.0;
+    const double xk = xc[k];
+    int seen = 0;
+    for (int p = cp[k]; p < cp[k + 1]; ++p) {
+        if (ri[p] == k) {
+            acc += (seen ? 0.0 : rowsum[k]) * xk;
+            seen = 1;
+        } else {
+            acc += v[p] * (xc[ri[p]] - xk);
+        }
+    }
+    return acc;
+}
+
+void orc_jacobi_diff(int n, const int* cp, const int* ri, const double* v, const double* rhs, double* x, double* tmp, int K,
+                     int iters, const double* omegas) {
+    double* rowsum = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    orc_rowsum(n, cp, v, rowsum);
+    for (int it = 0; it < iters; ++it) {
+        const double omega = omegas[it];
+        for (int c = 0; c < K; ++c) {
+            const double* xc = x + (size_t)c * n;
+            const double* bc = rhs + (size_t)c * n;
+            double* tc = tmp + (size_t)c * n;
+            for (int k = 0; k < n; ++k) {
+                double d = 0.0;
+                for (int p = cp[k]; p < cp[k + 1]; ++p)
+                    if (ri[p] == k) d += v[p];
+                const double acc = row_product_diff(cp, ri, v, rowsum, xc, k);
+                const double s = omega * (1.0 / d);
+                tc[k] = xc[k] + s * (bc[k] - acc);
+            }
+        }
+        memcpy(x, tmp, sizeof(double) * (size_t)n * K);
+    }
+    free(rowsum);
+}
+
+void orc_residual_diff(int n, const int* cp, const int* ri, const double* v, const double* b, const double* x, double* res,
+                       int K) {
+    double* rowsum = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    orc_rowsum(n, cp, v, rowsum);
+    for (int c = 0; c < K; ++c)
+        for (int i = 0; i < n; ++i)
+            res[(size_t)c * n + i] = b[(size_t)c * n + i] - row_product_diff(cp, ri, v, rowsum, x + (size_t)c * n, i);
+    free(rowsum);
+}
+
 /* ------------------------------------------------------------------ single operators */
 /* res = b - A*x (multigrid_solver.cpp:1066). */
 void orc_residual(int n, const int* cp, const int* ri, const double* v, const double* b, const double* x, double* res,
@@ -311,6 +390,31 @@ double orc_residual_check(int n, const int* cp, const int* ri, const double* v, 
         if (c == 0 || rel > best) best = rel;
     }
     free(r);
+    return type == 3 ? sqrt(frob) : best;
+}
+
+/* residualCheck with the cancellation-free row product (same norms, same association). */
+double orc_residual_check_diff(int n, const int* cp, const int* ri, const double* v, const double* b, const double* x, int K,
+                               int type, const double* mass) {
+    double* rowsum = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    orc_rowsum(n, cp, v, rowsum);
+    double best = 0.0, frob = 0.0;
+    for (int c = 0; c < K; ++c) {
+        const double* bc = b + (size_t)c * n;
+        double n1 = 0.0, n2 = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double ri_ = row_product_diff(cp, ri, v, rowsum, x + (size_t)c * n, i) - bc[i];
+            double w = 1.0;
+            if (type == 2) w = mass[i];
+            if (type == 1) w = mass[i] != 0.0 ? 1.0 / mass[i] : 0.0;
+            n1 += ri_ * (w * ri_);
+            n2 += bc[i] * (w * bc[i]);
+        }
+        frob += n1;
+        const double rel = sqrt(n1 / n2);
+        if (c == 0 || rel > best) best = rel;
+    }
+    free(rowsum);
     return type == 3 ? sqrt(frob) : best;
 }
 
@@ -544,12 +648,15 @@ int orc_setup(orc_solver* s, const int* cp, const int* ri, const double* v) {
     return status;
 }
 
-static void smooth(const orc_solver* s, const csc_t* A, const double* b, double* x, int K, int iters, const double* omegas) {
+static void smooth(const orc_solver* s, const csc_t* A, const double* b, double* x, int K, int iters, const double* omegas, int level) {
     if (s->smoother == 0) {
         orc_gauss_seidel(A->cols, A->colptr, A->rowidx, A->vals, b, x, K, iters);
     } else {
         double* tmp = (double*)malloc(sizeof(double) * (size_t)A->cols * K);
-        orc_jacobi(A->cols, A->colptr, A->rowidx, A->vals, b, x, tmp, K, iters, omegas);
+        if (s->row_product && level == 0)
+            orc_jacobi_diff(A->cols, A->colptr, A->rowidx, A->vals, b, x, tmp, K, iters, omegas);
+        else
+            orc_jacobi(A->cols, A->colptr, A->rowidx, A->vals, b, x, tmp, K, iters, omegas);
         free(tmp);
     }
 }
@@ -570,12 +677,15 @@ static void cycle(const orc_solver* s, const csc_t* A, const double* b, double* 
     }
     const csc_t* U = &s->U[k];
     const int nc = U->cols;
-    smooth(s, A, b, x, K, s->pre_iters, s->w_pre[k]);
+    smooth(s, A, b, x, K, s->pre_iters, s->w_pre[k], k);
     double* res = (double*)malloc(sizeof(double) * (size_t)n * K);
     double* rest = (double*)malloc(sizeof(double) * (size_t)nc * K);
     double* eps = (double*)calloc((size_t)nc * K, sizeof(double));
     for (int half = 0; half < (type == 0 ? 1 : 2); ++half) {
-        orc_residual(n, A->colptr, A->rowidx, A->vals, b, x, res, K);
+        if (s->smoother == 1 && s->row_product && k == 0)
+            orc_residual_diff(n, A->colptr, A->rowidx, A->vals, b, x, res, K);
+        else
+            orc_residual(n, A->colptr, A->rowidx, A->vals, b, x, res, K);
         orc_restrict(n, nc, U->colptr, U->rowidx, U->vals, res, rest, K);
         if (k == s->n_levels - 1) {
             double* work = (double*)malloc(sizeof(double) * (size_t)nc);
@@ -586,7 +696,7 @@ static void cycle(const orc_solver* s, const csc_t* A, const double* b, double* 
             cycle(s, &s->Abar[k + 1], rest, eps, K, k + 1, half == 0 ? type : (type == 1 ? 0 : 2));
         }
         orc_prolong_add(n, nc, U->colptr, U->rowidx, U->vals, eps, x, K);
-        smooth(s, A, b, x, K, s->post_iters, s->w_post[k]);
+        smooth(s, A, b, x, K, s->post_iters, s->w_post[k], k);
     }
     free(res), free(rest), free(eps);
 }
@@ -596,6 +706,7 @@ static void vcycle(const orc_solver* s, const csc_t* A, const double* b, double*
 }
 
 void orc_set_cycle_type(orc_solver* s, int cycle_type) { s->cycle_type = cycle_type; }
+void orc_set_row_product(orc_solver* s, int mode) { s->row_product = mode; }
 
 /* One V-cycle from level 0 after orc_setup (for cycle-level parity checks). */
 int orc_vcycle(orc_solver* s, const int* cp, const int* ri, const double* v, const double* b, double* x, int K) {
@@ -628,7 +739,9 @@ int orc_solve(orc_solver* s, const int* cp, const int* ri, const double* v, cons
     double residue;
     do {
         vcycle(s, &A, rhs, x, K, 0);
-        residue = orc_residual_check(s->n, cp, ri, v, rhs, x, K, s->criterion, s->mass);
+        residue = (s->smoother == 1 && s->row_product)
+                      ? orc_residual_check_diff(s->n, cp, ri, v, rhs, x, K, s->criterion, s->mass)
+                      : orc_residual_check(s->n, cp, ri, v, rhs, x, K, s->criterion, s->mass);
         if (hist_ms) hist_ms[iter] = now_ms() - t1;
         if (hist_res) hist_res[iter] = residue;
         ++iter;

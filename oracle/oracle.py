@@ -38,6 +38,11 @@ def _load():
     sig = {
         "orc_gauss_seidel": (None, [C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_int, C.c_int]),
         "orc_jacobi": (None, [C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, C.c_int, C.c_int, _f64p]),
+        "orc_jacobi_diff": (None, [C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, C.c_int, C.c_int, _f64p]),
+        "orc_residual_diff": (None, [C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, C.c_int]),
+        "orc_residual_check_diff": (C.c_double, [C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_int, C.c_int, _f64p]),
+        "orc_rowsum": (None, [C.c_int, _i32p, _f64p, _f64p]),
+        "orc_set_row_product": (None, [C.c_void_p, C.c_int]),
         "orc_set_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f64p, C.c_int, _f64p]),
         "orc_residual": (None, [C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, C.c_int]),
         "orc_restrict": (None, [C.c_int, C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_int]),
@@ -108,15 +113,26 @@ def gauss_seidel(A, b, x, iters):
     return np.ascontiguousarray(xx)
 
 
-def jacobi(A, b, x, iters, omega):
+def rowsum(A):
+    """Row sums of A accumulated with an error-free TwoSum chain (the device's level-0 setup)."""
+    n = A.shape[0]
+    cp, ri, v = _csc(A)
+    out = np.empty(n)
+    lib().orc_rowsum(n, _i(cp), _d(v), _d(out))
+    return out
+
+
+def jacobi(A, b, x, iters, omega, diff=False):
     """``iters`` damped-Jacobi sweeps x += omega_i D^-1 (b - A x) (the device smoother).
-    ``omega`` is one damping factor or a sequence with one entry per sweep."""
+    ``omega`` is one damping factor or a sequence with one entry per sweep. ``diff``: the
+    cancellation-free row product the device uses on the finest level."""
     n = A.shape[0]
     cp, ri, v = _csc(A)
     bb, xx = _colmajor(b, n), _colmajor(x, n)
     tmp = np.empty_like(xx)
     om = np.ascontiguousarray(np.broadcast_to(np.asarray(omega, dtype=np.float64), (int(iters),)))
-    lib().orc_jacobi(n, _i(cp), _i(ri), _d(v), _d(bb), _d(xx), _d(tmp), xx.shape[1], int(iters), _d(om))
+    fn = lib().orc_jacobi_diff if diff else lib().orc_jacobi
+    fn(n, _i(cp), _i(ri), _d(v), _d(bb), _d(xx), _d(tmp), xx.shape[1], int(iters), _d(om))
     return np.ascontiguousarray(xx)
 
 
@@ -134,13 +150,14 @@ def gershgorin_rho(A):
     return float((np.asarray(abs(A).sum(1)).ravel() / A.diagonal()).max())
 
 
-def residual(A, b, x):
-    """b - A x (multigrid_solver.cpp:1066)."""
+def residual(A, b, x, diff=False):
+    """b - A x (multigrid_solver.cpp:1066). ``diff``: the device's cancellation-free row product
+    (the matrix is then read by rows: column k of the CSC input is row k, as in the smoothers)."""
     n = A.shape[0]
     cp, ri, v = _csc(A)
     bb, xx = _colmajor(b, n), _colmajor(x, n)
     out = np.empty_like(xx)
-    lib().orc_residual(n, _i(cp), _i(ri), _d(v), _d(bb), _d(xx), _d(out), xx.shape[1])
+    (lib().orc_residual_diff if diff else lib().orc_residual)(n, _i(cp), _i(ri), _d(v), _d(bb), _d(xx), _d(out), xx.shape[1])
     return np.ascontiguousarray(out)
 
 
@@ -163,7 +180,7 @@ def prolong_add(U, eps, x):
     return np.ascontiguousarray(xx)
 
 
-def residual_check(A, b, x, type=2, mass_diag=None):
+def residual_check(A, b, x, type=2, mass_diag=None, diff=False):
     """residualCheck (multigrid_solver.cpp:1228-1277)."""
     n = A.shape[0]
     cp, ri, v = _csc(A)
@@ -171,8 +188,8 @@ def residual_check(A, b, x, type=2, mass_diag=None):
     m = np.ascontiguousarray(mass_diag, dtype=np.float64) if mass_diag is not None else None
     if type in (1, 2) and m is None:
         raise ValueError("types 1 and 2 need the mass diagonal")
-    return lib().orc_residual_check(n, _i(cp), _i(ri), _d(v), _d(bb), _d(xx), xx.shape[1], int(type),
-                                    _d(m) if m is not None else None)
+    fn = lib().orc_residual_check_diff if diff else lib().orc_residual_check
+    return fn(n, _i(cp), _i(ri), _d(v), _d(bb), _d(xx), xx.shape[1], int(type), _d(m) if m is not None else None)
 
 
 # --------------------------------------------------------------------------- the solver
@@ -182,7 +199,7 @@ class OracleSolver:
     ``'jacobi'`` is the op-for-op counterpart of the device path."""
 
     def __init__(self, mass, U, pre_iters=2, post_iters=2, max_iter=100, stopping_criteria=2, tolerance=1e-4,
-                 smoother="gs", omega=2.0 / 3.0, weights=None, cycle_type=0):
+                 smoother="gs", omega=2.0 / 3.0, weights=None, cycle_type=0, row_product="plain"):
         m = mass.diagonal() if sp.issparse(mass) else np.asarray(mass)
         self.mass = np.ascontiguousarray(m, dtype=np.float64)
         self.n = self.mass.shape[0]
@@ -196,6 +213,8 @@ class OracleSolver:
         lib().orc_set_params(self._h, int(pre_iters), int(post_iters), int(max_iter), int(stopping_criteria),
                              float(tolerance), {"gs": 0, "jacobi": 1}[smoother], float(omega))
         lib().orc_set_cycle_type(self._h, int(cycle_type))
+        # 'diff': the Jacobi variant evaluates A x on level 0 like the device does by default
+        lib().orc_set_row_product(self._h, {"plain": 0, "diff": 1}[row_product])
         self.convergence = []
         if weights is not None:  # {level: (pre_omegas, post_omegas)}
             for level, (pre, post) in dict(weights).items():

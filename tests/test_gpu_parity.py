@@ -9,6 +9,10 @@ Parity levels:
                   algorithm): both reach the tolerance; cycle counts and the residual-norm ratio
                   are recorded; both agree with a sparse direct solve.
   P4 invariants   Galerkin symmetry, monotone residual history, independence of launch mode.
+
+On the finest level the device evaluates A x in the cancellation-free form sum_{j != i} A_ij (x_j - x_i)
++ s_i x_i (option diff_form, on by default). The oracle's Jacobi variant has the same
+form (``diff=True`` / ``row_product="diff"``); the Gauss-Seidel reference path never uses it.
 """
 import numpy as np
 import pytest
@@ -45,7 +49,9 @@ def _weights(binding, n_levels):
 
 def _jacobi_oracle(p, solver, **kw):
     """The oracle running the device's own cycle: Jacobi sweeps with the device's dampings."""
-    return oracle.OracleSolver(p.M, p.U, smoother="jacobi", weights=_weights(solver.solver, len(p.U)), **kw)
+    diff = bool(solver.solver.get_option("diff_form"))
+    return oracle.OracleSolver(p.M, p.U, smoother="jacobi", weights=_weights(solver.solver, len(p.U)),
+                               row_product="diff" if diff else "plain", **kw)
 
 
 def _device_levels(s, n_levels):
@@ -64,12 +70,15 @@ def _rel_inf(a, b):
 
 
 # ------------------------------------------------------------------------------ P1: operators
-@pytest.mark.parametrize("mode", ["staged-exact", "staged-auto", "direct"])
+@pytest.mark.parametrize("mode", ["staged-exact", "staged-auto", "direct", "staged-exact-plain"])
 @pytest.mark.parametrize("K", [1, 3])
 @pytest.mark.parametrize("smoother", ["chebyshev", "jacobi"])
 def test_p1_operators_match_the_oracle(ico_small, mode, K, smoother):
     p = ico_small
     s, lhs, _ = _staged(p, K, smoother=smoother)
+    diff_form = not mode.endswith("-plain")
+    s.set_option("diff_form", diff_form)
+    mode = mode.replace("-plain", "")
     s.set_option("kernel_path", 1 if mode == "direct" else 0)
     s.set_option("lanes", 1 if mode == "staged-exact" else 0)
     s.stage(lhs, np.zeros((lhs.shape[0], K)))  # re-plan with the chosen kernel path
@@ -90,11 +99,12 @@ def test_p1_operators_match_the_oracle(ico_small, mode, K, smoother):
         n = A[k].shape[0]
         x = rng.standard_normal((n, K))
         b = rng.standard_normal((n, K))
-        check(s.level_op("residual", k, x, b), oracle.residual(A[k], b, x))
+        diff = diff_form and k == 0 and L > 0  # the finest level uses the cancellation-free row product
+        check(s.level_op("residual", k, x, b), oracle.residual(_rows(A[k]) if diff else A[k], b, x, diff=diff))
         if k < L:
             for sweeps in (1, 2, 3):  # level_op cycles through the pre-smoothing dampings
                 om = [W[k][0][i % len(W[k][0])] for i in range(sweeps)]
-                check(s.level_op("jacobi", k, x, b, sweeps=sweeps), oracle.jacobi(_rows(A[k]), b, x, sweeps, om))
+                check(s.level_op("jacobi", k, x, b, sweeps=sweeps), oracle.jacobi(_rows(A[k]), b, x, sweeps, om, diff=diff))
             U = p.U[k]
             e = rng.standard_normal((U.shape[1], K))
             check(s.level_op("restrict", k, x), oracle.restrict(U, x))
@@ -113,7 +123,7 @@ def test_p1_operators_on_a_larger_mesh(torus_mid, path):
     x = rng.standard_normal((n, 1))
     b = rng.standard_normal((n, 1))
     got = s.level_op("jacobi", 0, x, b, sweeps=2)
-    want = oracle.jacobi(lhs, b, x, 2, _weights(s, 1)[0][0])
+    want = oracle.jacobi(lhs, b, x, 2, _weights(s, 1)[0][0], diff=True)
     if path == 0:
         np.testing.assert_array_equal(got, want)
     else:
@@ -373,6 +383,12 @@ def test_residual_types(ico_small, type_, K):
     got = p.solver.residual(p.lhs, b, x, type_)
     want = oracle.residual_check(p.lhs, b, x, type_, p.m)
     assert got == pytest.approx(want, rel=1e-12)
+    assert got == pytest.approx(oracle.residual_check(p.lhs, b, x, type_, p.m, diff=True), rel=1e-13)
+    p.solver.solver.set_option("diff_form", 0)
+    try:
+        assert p.solver.residual(p.lhs, b, x, type_) == pytest.approx(want, rel=1e-13)
+    finally:
+        p.solver.solver.set_option("diff_form", 1)
 
 
 # ------------------------------------------------------------------------------ P4 / behaviour

@@ -237,3 +237,63 @@ def test_at_least_one_cycle_and_max_iter(ico_small):
     o = oracle.OracleSolver(p.M, p.U, tolerance=0.0, max_iter=3)
     o.solve(p.lhs, p.rhs)
     assert o.solver_timing["iterations"] == 3
+
+
+# ------------------------------------------------------------------------------ cancellation-free row product
+def test_rowsum_is_exact(ico_small):
+    """orc_rowsum (TwoSum chain) against exact rational arithmetic: the row sums of tau M + S are ~1e-9
+    next to entries ~1, a plain fp64 sum loses many digits of them."""
+    from fractions import Fraction
+
+    p = ico_small
+    A = sp.csr_matrix(p.lhs)
+    got = oracle.rowsum(A)
+    for i in list(range(0, A.shape[0], 97)) + [A.shape[0] - 1]:
+        exact = sum((Fraction(float(v)) for v in A.data[A.indptr[i]:A.indptr[i + 1]]), Fraction(0))
+        assert got[i] == float(exact)  # correctly rounded
+    plain = np.asarray(A.sum(1)).ravel()
+    assert np.abs(plain - got).max() > 1e-7 * np.abs(got).min()  # the plain sum loses digits (1e-3 of them at 1 M vertices)
+
+
+@pytest.mark.parametrize("K", [1, 3])
+def test_diff_row_product_is_the_same_operator(ico_small, K):
+    """sum_{j != i} A_ij (x_j - x_i) + s_i x_i is A x: equal to the plain operators to rounding on
+    generic vectors, and far more accurate on x = large constant + small variation."""
+    p = ico_small
+    rng = np.random.default_rng(21)
+    n = p.lhs.shape[0]
+    x = rng.standard_normal((n, K))
+    b = rng.standard_normal((n, K))
+    scale = np.abs(p.lhs).sum(1).max() * np.abs(x).max()
+    assert np.abs(oracle.residual(p.lhs, b, x, diff=True) - oracle.residual(p.lhs, b, x)).max() <= 8 * np.finfo(float).eps * scale
+    om = [0.8, 0.5]
+    assert np.abs(oracle.jacobi(p.lhs, b, x, 2, om, diff=True) - oracle.jacobi(p.lhs, b, x, 2, om)).max() <= 1e-13 * np.abs(x).max()
+    for t in range(4):
+        assert oracle.residual_check(p.lhs, b, x, t, p.m, diff=True) == pytest.approx(oracle.residual_check(p.lhs, b, x, t, p.m), rel=1e-13)
+    # x = c + y with c = 1e6 |y|: A x = c s + A y; compare both forms with exact row-by-row arithmetic
+    from fractions import Fraction
+
+    A = sp.csr_matrix(p.lhs)
+    y = rng.standard_normal((n, 1))
+    xc = 1e6 + y
+    zero = np.zeros((n, 1))
+    plain = -oracle.residual(p.lhs, zero, xc)
+    diff = -oracle.residual(p.lhs, zero, xc, diff=True)
+    err_plain = err_diff = 0.0
+    for i in range(0, n, 61):
+        sl = slice(A.indptr[i], A.indptr[i + 1])
+        exact = float(sum((Fraction(float(v)) * Fraction(float(xc[j, 0])) for v, j in zip(A.data[sl], A.indices[sl])), Fraction(0)))
+        err_plain = max(err_plain, abs(plain[i, 0] - exact))
+        err_diff = max(err_diff, abs(diff[i, 0] - exact))
+    assert err_diff <= 1e-14 and err_plain >= 1e3 * err_diff, (err_plain, err_diff)
+
+
+def test_jacobi_oracle_with_diff_row_product_solves(ico10k):
+    p = ico10k
+    plain = oracle.OracleSolver(p.M, p.U, tolerance=1e-6, smoother="jacobi")
+    diff = oracle.OracleSolver(p.M, p.U, tolerance=1e-6, smoother="jacobi", row_product="diff")
+    xp, xd = plain.solve(p.lhs, p.rhs), diff.solve(p.lhs, p.rhs)
+    assert plain.solver_timing["iterations"] == diff.solver_timing["iterations"]
+    # the constant component of x is (1^T b) / (1^T A 1): it sees the row sums at full relative accuracy
+    assert p.mnorm(xp - xd) <= 1e-6 * p.mnorm(xp)
+    assert oracle.residual_check(p.lhs, p.rhs, xd, 2, p.m) <= 1e-6
