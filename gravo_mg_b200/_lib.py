@@ -92,6 +92,16 @@ SIGNATURES = {
     "gmg_reset_kernel_profile": (C.c_int, [_h]),
     "gmg_last_launch_count": (C.c_int, [_h, _i64p]),
     "gmg_get_trace": (C.c_int, [_h, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _i64p]),
+    "gmg_update_values_device": (C.c_int, [_h, C.c_void_p, C.c_void_p, C.c_int32]),
+    "gmg_fetch_solution_device": (C.c_int, [_h, C.c_void_p]),
+    "gmg_mesh_attach": (C.c_int, [_h, C.c_int64, _i32p]),
+    "gmg_mesh_set_positions": (C.c_int, [_h, _f64p]),
+    "gmg_mesh_stiffness": (C.c_int, [_h]),
+    "gmg_mesh_mass": (C.c_int, [_h, C.c_int32]),
+    "gmg_mesh_system": (C.c_int, [_h, C.c_double, C.c_double, _f64p, C.c_int32]),
+    "gmg_mesh_flow": (C.c_int, [_h, C.c_double, C.c_int32, C.c_int32]),
+    "gmg_mesh_get": (C.c_int, [_h, C.c_int32, _f64p]),
+    "gmg_mesh_pattern": (C.c_int, [C.c_int64, C.c_int64, _i32p, _i32p, _i32p, _i64p]),
 }
 
 

@@ -150,6 +150,81 @@ class MultigridSolver:
         check(self._h, lib.gmg_fetch_solution(self._h, f64(x)))
         return x
 
+    # ------------------------------------------------------------------ device-resident systems (additions)
+    def solve_device(self, values, rhs, out=None):
+        """Solve with the lhs VALUES (CSR order of the staged pattern) and the right-hand side already on
+        the GPU: ``values`` (nnz,) and ``rhs`` (N, K) are float64 CUDA torch tensors on the solver's device
+        (torch is the plumbing for device memory; the C ABI takes raw device pointers). Returns the
+        solution as a CUDA tensor. The pattern comes from an earlier ``solve`` / ``stage`` / ``attach_mesh``."""
+        import torch
+
+        if not (values.is_cuda and rhs.is_cuda and values.dtype == torch.float64 and rhs.dtype == torch.float64):
+            raise TypeError("solve_device expects float64 CUDA tensors")
+        values = values.contiguous()
+        b = rhs.contiguous()
+        if b.dim() == 1:
+            b = b[:, None]
+        if b.shape[0] != self._n:
+            raise ValueError(f"expected a right-hand side with {self._n} rows")
+        nnz = self.level_info()[0]["nnz_a"]
+        if values.numel() != nnz:
+            raise ValueError(f"expected {nnz} values (CSR order of the staged pattern), got {values.numel()}")
+        torch.cuda.current_stream(values.device).synchronize()  # the library copies on its own stream
+        check(self._h, lib.gmg_update_values_device(self._h, values.data_ptr(), b.data_ptr(), b.shape[1]))
+        self._staged_shape = tuple(b.shape)
+        check(self._h, lib.gmg_solve_staged(self._h))
+        x = torch.empty_like(b) if out is None else out
+        check(self._h, lib.gmg_fetch_solution_device(self._h, x.data_ptr()))
+        return x
+
+    # ------------------------------------------------------------------ mesh operators on the device (additions)
+    MASS_TYPES = {"barycentric": 0, "voronoi": 1}
+
+    def attach_mesh(self, faces, positions=None):
+        """Stage the mesh's sparsity pattern (vertex adjacency + diagonal) and the gather lists of the
+        device-side assembly; optionally upload vertex positions."""
+        F = as_i32(faces)
+        if F.ndim != 2 or F.shape[1] != 3:
+            raise ValueError("faces must have shape (nf, 3)")
+        check(self._h, lib.gmg_mesh_attach(self._h, F.shape[0], i32(F)))
+        if positions is not None:
+            self.set_positions(positions)
+
+    def set_positions(self, positions):
+        P = as_f64(positions)
+        if P.shape != (self._n, 3):
+            raise ValueError(f"positions must have shape ({self._n}, 3)")
+        check(self._h, lib.gmg_mesh_set_positions(self._h, f64(P)))
+
+    def mesh_stiffness(self):
+        check(self._h, lib.gmg_mesh_stiffness(self._h))
+
+    def mesh_mass(self, type="voronoi"):
+        check(self._h, lib.gmg_mesh_mass(self._h, self.MASS_TYPES[type] if isinstance(type, str) else int(type)))
+
+    def mesh_system(self, alpha, beta, y=None):
+        """lhs = alpha M + beta S, rhs = M y (y=None: the resident positions) staged for ``solve_staged``."""
+        if y is None:
+            check(self._h, lib.gmg_mesh_system(self._h, float(alpha), float(beta), None, 3))
+            self._staged_shape = (self._n, 3)
+        else:
+            Y = _dense_rhs(y, self._n)
+            check(self._h, lib.gmg_mesh_system(self._h, float(alpha), float(beta), f64(Y), Y.shape[1]))
+            self._staged_shape = Y.shape
+
+    def mesh_flow(self, tau, steps, mass="barycentric"):
+        """``steps`` conformal-flow steps on the device (demos/conformal_flow.py:54-59)."""
+        check(self._h, lib.gmg_mesh_flow(self._h, float(tau), self.MASS_TYPES[mass] if isinstance(mass, str) else int(mass), int(steps)))
+        self._staged_shape = (self._n, 3)
+
+    def mesh_get(self, which):
+        which = {"positions": 0, "stiffness": 1, "mass": 2, "lhs": 3, "rhs": 4}[which] if isinstance(which, str) else int(which)
+        nnz = self.level_info()[0]["nnz_a"]
+        shape = {0: (self._n, 3), 1: (nnz,), 2: (self._n,), 3: (nnz,), 4: getattr(self, "_staged_shape", (self._n, 3))}[which]
+        out = np.empty(shape)
+        check(self._h, lib.gmg_mesh_get(self._h, which, f64(out)))
+        return out
+
     # ------------------------------------------------------------------ data access
     def prolongation_matrices(self):
         count = C.c_int32()

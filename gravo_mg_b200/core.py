@@ -122,6 +122,25 @@ class MultigridSolver(object):
         global ``lhs`` / ``rhs`` and gets the full solution back."""
         self.solver.distribute(replicate_rows)
 
+    # Additions: device-resident systems and operator assembly on the device (SURVEY §8 f1 / f3).
+    def solve_device(self, values, rhs, out=None):
+        """``solve`` with the lhs values (CSR order of the staged pattern) and rhs already on the GPU
+        (float64 CUDA torch tensors); returns a CUDA tensor. See bindings.MultigridSolver.solve_device."""
+        return self.solver.solve_device(values, rhs, out)
+
+    def attach_mesh(self, faces, positions=None):
+        """Triangle faces (nf, 3) of the mesh the solver was built on: stiffness, mass, lhs = a M + b S,
+        rhs = M y and normalize_area then run as kernels on the resident mesh (``mesh_*`` methods of
+        ``self.solver``; ``conformal_flow`` below)."""
+        self.solver.attach_mesh(faces, positions)
+
+    def conformal_flow(self, steps, tau=0.01, mass="barycentric"):
+        """demos/conformal_flow.py:54-59 on the device: ``steps`` times M_t = mass(V_t), lhs = M_t + tau S,
+        rhs = M_t V_t, V = normalize_area(solve(lhs, rhs)). Needs ``attach_mesh(F, V)`` and
+        ``self.solver.mesh_stiffness()`` first. Returns the new vertex positions (N, 3)."""
+        self.solver.mesh_flow(tau, steps, mass)
+        return self.solver.mesh_get("positions")
+
     # Additions: the maps the CSV writers dump, as Python objects.
     @property
     def hierarchy_timing(self):

@@ -8,6 +8,7 @@
 #include <stdexcept>
 #include <string>
 
+#include "mesh_assembly.h"
 #include "nccl_dl.h"
 #include "solver.h"
 
@@ -355,6 +356,77 @@ int gmg_residual(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t
     return guarded(h, [&] {
         require(a_indptr && a_indices && a_data && rhs && x && out, "null argument");
         *out = engine(h).residual(n, a_indptr, a_indices, a_data, rhs, x, K, type);
+    });
+}
+
+// ---- device-resident systems and mesh assembly ------------------------------------------------
+int gmg_update_values_device(gmg_handle h, const double* d_a_data, const double* d_rhs, int32_t K) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(d_a_data && d_rhs, "null argument");
+        engine(h).update_values_device(d_a_data, d_rhs, K);
+    });
+}
+
+int gmg_fetch_solution_device(gmg_handle h, double* d_x_out) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(d_x_out != nullptr, "null argument");
+        engine(h).fetch_solution_device(d_x_out);
+    });
+}
+
+int gmg_mesh_attach(gmg_handle h, int64_t nf, const int32_t* faces) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(faces != nullptr && nf > 0, "faces are required");
+        engine(h).mesh_attach(nf, faces);
+    });
+}
+
+int gmg_mesh_set_positions(gmg_handle h, const double* pos) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(pos != nullptr, "null argument");
+        engine(h).mesh_set_positions(pos);
+    });
+}
+
+int gmg_mesh_stiffness(gmg_handle h) {
+    if (!h) return 1;
+    return guarded(h, [&] { engine(h).mesh_stiffness(); });
+}
+
+int gmg_mesh_mass(gmg_handle h, int32_t type) {
+    if (!h) return 1;
+    return guarded(h, [&] { engine(h).mesh_mass(type); });
+}
+
+int gmg_mesh_system(gmg_handle h, double alpha, double beta, const double* y, int32_t K) {
+    if (!h) return 1;
+    return guarded(h, [&] { engine(h).mesh_system(alpha, beta, y, K); });
+}
+
+int gmg_mesh_flow(gmg_handle h, double tau, int32_t mass_type, int32_t steps) {
+    if (!h) return 1;
+    return guarded(h, [&] { engine(h).mesh_flow(tau, mass_type, steps); });
+}
+
+int gmg_mesh_get(gmg_handle h, int32_t which, double* out) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(out != nullptr, "null argument");
+        engine(h).mesh_get(which, out);
+    });
+}
+
+int gmg_mesh_pattern(int64_t n, int64_t nf, const int32_t* faces, int32_t* indptr, int32_t* indices, int64_t* nnz) {
+    return guarded(nullptr, [&] {
+        require(faces && indptr && nnz, "null argument");
+        const gmg::MeshTopology t = gmg::build_mesh_topology(n, nf, faces);
+        *nnz = t.pattern.nnz();
+        std::copy(t.pattern.indptr.begin(), t.pattern.indptr.end(), indptr);
+        if (indices) std::copy(t.pattern.indices.begin(), t.pattern.indices.end(), indices);
     });
 }
 

@@ -10,6 +10,7 @@
 
 #include "dense_coarse.h"
 #include "host_xfer.h"
+#include "mesh_assembly.h"
 #include "nccl_dl.h"
 #include "peer_exchange.h"
 #include "solver.h"
@@ -212,6 +213,12 @@ public:
         const bool uploaded = same && xf;
         if (!same) {
             GMG_CUDA(cudaStreamSynchronize(stream_));  // a speculative upload may still be in flight
+            // a new pattern is checked once (repeated solves compare against the checked copy): the symbolic
+            // products and the kernels index with these arrays
+            for (int64_t r = 0; r < n; ++r)
+                if (indptr[r + 1] < indptr[r]) throw std::invalid_argument("lhs indptr must be non-decreasing");
+            for (int64_t q = 0; q < nnz; ++q)
+                if (indices[q] < 0 || indices[q] >= n) throw std::invalid_argument("lhs column index out of range");
             setup_pattern(n, indptr, indices);
         }
         if (!uploaded) {
@@ -269,6 +276,147 @@ public:
         st_->transfer_timing["d2h_bytes"] = (double)(count * sizeof(double));
     }
 
+    // ------------------------------------------------------------------ device-resident systems
+    // The staged pattern stays; only values and right-hand side change, and they are already in HBM
+    // (assembled by the caller's own kernels or by the mesh functions below): device-to-device copies
+    // on the solver stream, no host staging.
+    void update_values_device(const double* d_vals, const double* d_rhs, int K) override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        if (!pattern_ready_ || !hierarchy_ready_) throw std::logic_error("update_values_device needs a staged sparsity pattern (stage a system or attach a mesh first)");
+        if (st_->dist.world > 1) throw std::logic_error("update_values_device is single-GPU");
+        set_columns(K);
+        cudaPointerAttributes pa;
+        for (const void* ptr : {(const void*)d_vals, (const void*)d_rhs}) {
+            GMG_CUDA(cudaPointerGetAttributes(&pa, ptr));
+            if (pa.type != cudaMemoryTypeDevice && pa.type != cudaMemoryTypeManaged) throw std::invalid_argument("update_values_device expects device pointers");
+        }
+        GMG_CUDA(cudaMemcpyAsync(lv_[0].A.v64.ptr, d_vals, (size_t)lv_[0].A.nnz * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+        GMG_CUDA(cudaMemcpyAsync(rhs64_.ptr, d_rhs, (size_t)st_->n * K * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+        mark_staged_on_device();
+    }
+
+    void fetch_solution_device(double* d_x) override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        if (!solved_) throw std::logic_error("fetch_solution before solve_staged");
+        if (st_->dist.world > 1) throw std::logic_error("fetch_solution_device is single-GPU");
+        GMG_CUDA(cudaMemcpyAsync(d_x, solution_device(), (size_t)st_->n * K_ * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+    }
+
+    // ------------------------------------------------------------------ mesh operators on the device
+    void mesh_attach(int64_t nf, const int* faces) override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        if (st_->dist.world > 1) throw std::logic_error("mesh assembly is single-GPU");
+        const MeshTopology topo = build_mesh_topology(st_->n, nf, faces);
+        if (indptr_changed(topo.pattern.indptr.data(), topo.pattern.indices.data(), st_->n)) {
+            GMG_CUDA(cudaStreamSynchronize(stream_));
+            setup_pattern(st_->n, topo.pattern.indptr.data(), topo.pattern.indices.data());
+        }
+        mesh_.attach(topo, faces, stream_);
+        mesh_pos_.ensure((size_t)st_->n * 3), mesh_m_.ensure((size_t)st_->n), mesh_s_.ensure((size_t)lv_[0].A.nnz);
+        mesh_has_pos_ = mesh_has_s_ = mesh_has_m_ = false;
+    }
+
+    void mesh_set_positions(const double* pos) override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        require_mesh();
+        GMG_CUDA(cudaMemcpyAsync(mesh_pos_.ptr, pos, (size_t)st_->n * 3 * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+        mesh_has_pos_ = true;
+    }
+
+    void mesh_stiffness() override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        require_mesh(true);
+        mesh_.face_geometry(mesh_pos_.ptr, MESH_MASS_BARYCENTRIC, stream_);
+        mesh_.stiffness(lv_[0].A.indptr.ptr, lv_[0].A.indices.ptr, mesh_s_.ptr, stream_);
+        mesh_has_s_ = true;
+    }
+
+    void mesh_mass(int type) override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        require_mesh(true);
+        if (type != MESH_MASS_BARYCENTRIC && type != MESH_MASS_VORONOI) throw std::invalid_argument("mass type must be 0 (barycentric) or 1 (Voronoi)");
+        mesh_.face_geometry(mesh_pos_.ptr, type, stream_);
+        mesh_.mass(mesh_m_.ptr, stream_);
+        mesh_has_m_ = true;
+    }
+
+    // lhs = alpha M + beta S, rhs = M Y staged for solve_staged(); Y = the host array y (n x K) or, when y is
+    // null, the resident vertex positions (K = 3).
+    void mesh_system(double alpha, double beta, const double* y, int K) override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        require_mesh(true);
+        if (!mesh_has_s_ || !mesh_has_m_) throw std::logic_error("mesh_system needs mesh_stiffness and mesh_mass first");
+        if (!y) K = 3;
+        set_columns(K);
+        const double* yd = mesh_pos_.ptr;
+        if (y) {
+            mesh_y_.upload(y, (size_t)st_->n * K, stream_);
+            yd = mesh_y_.ptr;
+        }
+        mesh_.system(lv_[0].A.indptr.ptr, lv_[0].A.indices.ptr, alpha, beta, mesh_s_.ptr, mesh_m_.ptr, yd, K, lv_[0].A.v64.ptr,
+                     rhs64_.ptr, stream_);
+        if (y) GMG_CUDA(cudaStreamSynchronize(stream_));  // the caller's buffer has been read
+        mark_staged_on_device();
+    }
+
+    // demos/conformal_flow.py:54-59 without leaving the GPU: per step M_t = mass(V_t), lhs = M_t + tau S,
+    // rhs = M_t V_t, V_{t+1} = normalize_area(solve(lhs, rhs)); S is the resident stiffness (fixed, as upstream).
+    void mesh_flow(double tau, int mass_type, int steps) override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        require_mesh(true);
+        if (!mesh_has_s_) throw std::logic_error("mesh_flow needs mesh_stiffness first");
+        if (steps < 0) throw std::invalid_argument("steps must be >= 0");
+        cudaEvent_t e[4];
+        for (auto& ev : e) GMG_CUDA(cudaEventCreate(&ev));
+        double t_asm = 0, t_norm = 0, t_red = 0, t_fac = 0, t_cyc = 0, iters = 0;
+        try {
+            for (int it = 0; it < steps; ++it) {
+                GMG_CUDA(cudaEventRecord(e[0], stream_));
+                mesh_mass(mass_type);
+                mesh_system(1.0, tau, nullptr, 3);
+                GMG_CUDA(cudaEventRecord(e[1], stream_));
+                solve_staged();
+                GMG_CUDA(cudaEventRecord(e[2], stream_));
+                mesh_.normalize_area(solution_device(), mesh_pos_.ptr, stream_);
+                GMG_CUDA(cudaEventRecord(e[3], stream_));
+                GMG_CUDA(cudaStreamSynchronize(stream_));
+                float a = 0, b = 0;
+                GMG_CUDA(cudaEventElapsedTime(&a, e[0], e[1]));
+                GMG_CUDA(cudaEventElapsedTime(&b, e[2], e[3]));
+                t_asm += a, t_norm += b;
+                const auto& tm = st_->solver_timing;
+                t_red += tm.at("reduction"), t_fac += tm.at("coarsest_solve"), t_cyc += tm.at("cycles"), iters += tm.at("iterations");
+            }
+        } catch (...) {
+            for (auto& ev : e) cudaEventDestroy(ev);
+            throw;
+        }
+        for (auto& ev : e) cudaEventDestroy(ev);
+        auto& tt = st_->transfer_timing;
+        tt["flow_steps"] = steps, tt["flow_assemble_ms"] = t_asm, tt["flow_normalize_ms"] = t_norm, tt["flow_reduction_ms"] = t_red;
+        tt["flow_factor_ms"] = t_fac, tt["flow_cycles_ms"] = t_cyc, tt["flow_iterations"] = iters;
+    }
+
+    void mesh_get(int which, double* out) override {
+        GMG_CUDA(cudaSetDevice(st_->params.device));
+        require_mesh();
+        const double* src = nullptr;
+        size_t count = 0;
+        switch (which) {
+            case 0: src = mesh_pos_.ptr, count = (size_t)st_->n * 3; if (!mesh_has_pos_) src = nullptr; break;
+            case 1: src = mesh_s_.ptr, count = (size_t)lv_[0].A.nnz; if (!mesh_has_s_) src = nullptr; break;
+            case 2: src = mesh_m_.ptr, count = (size_t)st_->n; if (!mesh_has_m_) src = nullptr; break;
+            case 3: src = lv_[0].A.v64.ptr, count = (size_t)lv_[0].A.nnz; if (!staged_) src = nullptr; break;
+            case 4: src = rhs64_.ptr, count = (size_t)st_->n * K_; if (!staged_) src = nullptr; break;
+            default: throw std::invalid_argument("mesh_get: which must be 0..4");
+        }
+        if (!src) throw std::logic_error("mesh_get: that array has not been computed yet");
+        GMG_CUDA(cudaMemcpyAsync(out, src, count * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+    }
+
     // ------------------------------------------------------------------ solve
     void solve_staged() override {
         GMG_CUDA(cudaSetDevice(st_->params.device));
@@ -277,6 +425,8 @@ public:
         const gmg_params& p = st_->params;
         if (p.cycle_type < 0 || p.cycle_type > 2) throw std::invalid_argument("cycle_type must be 0 (V), 1 (F) or 2 (W)");
         if (p.cycle_type != 0 && st_->dist.world > 1) throw std::invalid_argument("F- and W-cycles are single-GPU for now");
+        if (sizeof(T) == 4 && st_->dist.world > 1)
+            throw std::invalid_argument("dtype float32 is single-GPU for now: the fp64 defect correction that lets fp32 levels reach a 1e-4 tolerance is not sharded");
         if (p.max_iter < 1) throw std::invalid_argument("max_iter must be >= 1");
         if (p.stopping_criteria < 0 || p.stopping_criteria > 3) throw std::invalid_argument("stopping_criteria must be 0..3");
         if (hist_res_.count < (size_t)p.max_iter) {
@@ -712,6 +862,7 @@ private:
     // of A_k U_k and of every Galerkin operator, build the row-tile plans for this rank's row
     // ranges, the halo index lists and the coarse workspace.
     void setup_pattern(int64_t n, const int* indptr, const int* indices) {
+        mesh_.detach();  // gather lists of an attached mesh belong to the pattern being replaced
         const auto& U = st_->hier.U;
         n_levels_ = (int)U.size();
         if (n_levels_ + 1 > kMaxLevels) throw std::invalid_argument("too many levels");
@@ -1047,6 +1198,46 @@ private:
         cudaFree(arena_);
         arena_ = nullptr, arena_bytes_ = 0;
         drop_graphs();
+    }
+
+    void require_mesh(bool need_positions = false) const {
+        if (!mesh_.attached() || !pattern_ready_) throw std::logic_error("no mesh attached (gmg_mesh_attach)");
+        if (need_positions && !mesh_has_pos_) throw std::logic_error("no vertex positions on the device (gmg_mesh_set_positions)");
+    }
+
+    // K right-hand sides from now on (vectors re-allocated, cycle rebuilt when it changes).
+    void set_columns(int K) {
+        if (K < 1 || K > kMaxRhsTile * kMaxNormChunks) throw std::invalid_argument("number of right-hand sides must be 1..32");
+        if (K != K_) {
+            K_ = K;
+            if (pattern_ready_) allocate_vectors();
+            invalidate_cycle();
+        }
+    }
+
+    // Is (indptr, indices) different from the staged level-0 pattern (or is nothing staged)?
+    bool indptr_changed(const int* indptr, const int* indices, int64_t n) const {
+        if (!pattern_ready_ || !hierarchy_ready_ || st_->a_pat.empty() || st_->a_pat[0].rows != n) return true;
+        const int64_t nnz = indptr[n];
+        if ((int64_t)st_->a_pat[0].indices.size() != nnz) return true;
+        return std::memcmp(st_->a_pat[0].indptr.data(), indptr, (n + 1) * sizeof(int)) != 0 ||
+               std::memcmp(st_->a_pat[0].indices.data(), indices, nnz * sizeof(int)) != 0;
+    }
+
+    // Values and rhs of the system were written by device work queued on stream_.
+    void mark_staged_on_device() {
+        numeric_ready_ = false;
+        rhs_pending_ = false;
+        staged_ = true;
+        solved_ = false;
+        st_->transfer_timing["h2d_bytes"] = 0.0;
+        st_->transfer_timing["pattern_reused"] = 1.0;
+    }
+
+    // The fp64 solution of the last solve, in HBM.
+    const double* solution_device() {
+        if (sizeof(T) == 4 && !refine()) launch_cast_f32_f64(reinterpret_cast<const float*>(x_final_), x64_.ptr, (size_t)st_->n * K_, stream_);
+        return sizeof(T) == 4 ? x64_.ptr : reinterpret_cast<const double*>(x_final_);
     }
 
     void set_initial_guess() {
@@ -1656,6 +1847,9 @@ private:
     DeviceBuffer<T> weights_;
     DeviceBuffer<int> q_indptr_, q_indices_;
     DeviceBuffer<double> q_vals_, q_b_, q_x_, q_vd_, q_dinv_, q_rho_;
+    MeshAssembler mesh_;               // device-side operator assembly (mesh_assembly.h)
+    DeviceBuffer<double> mesh_pos_, mesh_s_, mesh_m_, mesh_y_;
+    bool mesh_has_pos_ = false, mesh_has_s_ = false, mesh_has_m_ = false;
     std::vector<DevHalo> halo_[3];
     size_t max_halo_ = 0;
     DeviceBuffer<T> halo_send_, halo_recv_;

@@ -35,6 +35,17 @@ public:
     virtual bool level_info(int level, int64_t* rows, int64_t* nnz_a, int64_t* nnz_u) = 0;
     virtual void kernel_profile(int kind, int level, double* total_ms, int64_t* launches) = 0;
     virtual void reset_kernel_profile() = 0;
+    // ---- device-resident systems: values and right-hand side already in HBM
+    virtual void update_values_device(const double* d_vals, const double* d_rhs, int K) = 0;
+    virtual void fetch_solution_device(double* d_x) = 0;
+    // ---- operator assembly on the device for triangle meshes (mesh_assembly.h)
+    virtual void mesh_attach(int64_t nf, const int* faces) = 0;
+    virtual void mesh_set_positions(const double* pos) = 0;
+    virtual void mesh_stiffness() = 0;
+    virtual void mesh_mass(int type) = 0;
+    virtual void mesh_system(double alpha, double beta, const double* y, int K) = 0;
+    virtual void mesh_flow(double tau, int mass_type, int steps) = 0;
+    virtual void mesh_get(int which, double* out) = 0;  // 0 positions n x 3, 1 S values, 2 mass, 3 lhs values, 4 rhs n x K
 };
 
 struct SolverState {

@@ -209,8 +209,8 @@ __device__ __forceinline__ void fused_stopping_test(const double* partials, unsi
     }
 }
 
-// Own-row operands of the epilogue. They do not depend on the row product, so the staged kernel
-// loads them before it waits for the tile's slab (their latency hides behind the bulk copy).
+// Own-row operands of the epilogue. The row index comes from the tile descriptor in the stage, so they are
+// requested right after the stage's full-barrier wait, together with the gathers of the row (one round trip).
 template <typename T, int K>
 struct RowOperands {
     T b[K];

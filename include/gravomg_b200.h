@@ -133,6 +133,43 @@ int gmg_fetch_solution(gmg_handle h, double* x_out);
 int gmg_residual(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t* a_indices, const double* a_data,
                  const double* rhs, const double* x, int32_t K, int32_t type, double* out);
 
+/* ---- device-resident systems: the values of lhs (same sparsity pattern as the staged
+ * system, CSR order) and the right-hand side (n x K) are already in HBM — assembled by the caller's own
+ * kernels — and the solution is wanted there too. Replaces the host->device staging of gmg_solve for
+ * repeated-solve loops (demos/conformal_flow.py:54-59); gmg_solve_staged in between. d_* are device
+ * pointers of the handle's device; the copies are device-to-device on the solver's stream. */
+int gmg_update_values_device(gmg_handle h, const double* d_a_data, const double* d_rhs, int32_t K);
+int gmg_fetch_solution_device(gmg_handle h, double* d_x_out);
+
+/* ---- operator assembly on the device for triangle meshes ----
+ * What the reference's callers compute on the host around every solve — S = -igl.cotmatrix(V, F),
+ * M = igl.massmatrix(V, F, type), lhs = alpha M + beta S, rhs = M Y, V = normalize_area(x)
+ * (demos/smoothing.py:28-30, 43-47; demos/conformal_flow.py:22-24, 54-59;
+ * experiments/python/comparisons.py:39-55, 75-79; gravomg/util.py:46-55) — as kernels on the resident mesh.
+ *   gmg_mesh_attach         faces (nf x 3, int32) -> sparsity pattern (vertex adjacency + diagonal, sorted)
+ *                           staged on the device with its symbolic Galerkin setup, gather lists for assembly
+ *   gmg_mesh_set_positions  vertex positions n x 3 (host) -> device
+ *   gmg_mesh_stiffness      S from the resident positions (kept until recomputed)
+ *   gmg_mesh_mass           lumped mass from the resident positions; type 0 barycentric, 1 mixed Voronoi
+ *   gmg_mesh_system         lhs = alpha M + beta S, rhs = M Y staged for gmg_solve_staged; Y = y (host, n x K)
+ *                           or, with y == NULL, the resident positions (K = 3)
+ *   gmg_mesh_flow           `steps` conformal-flow steps without leaving the GPU: M_t = mass(V_t),
+ *                           lhs = M_t + tau S, rhs = M_t V_t, V_{t+1} = normalize_area(solve(lhs, rhs));
+ *                           totals in timing map 2: flow_assemble_ms, flow_reduction_ms, flow_factor_ms,
+ *                           flow_cycles_ms, flow_normalize_ms, flow_iterations
+ *   gmg_mesh_get            which: 0 positions (n x 3), 1 S values (nnz, CSR order of the pattern), 2 mass (n),
+ *                           3 lhs values (nnz), 4 rhs (n x K) -> host
+ *   gmg_mesh_pattern        host only, no handle: the pattern gmg_mesh_attach stages. Query nnz with
+ *                           indices == NULL (indptr needs n + 1 slots). */
+int gmg_mesh_attach(gmg_handle h, int64_t nf, const int32_t* faces);
+int gmg_mesh_set_positions(gmg_handle h, const double* pos);
+int gmg_mesh_stiffness(gmg_handle h);
+int gmg_mesh_mass(gmg_handle h, int32_t type);
+int gmg_mesh_system(gmg_handle h, double alpha, double beta, const double* y, int32_t K);
+int gmg_mesh_flow(gmg_handle h, double tau, int32_t mass_type, int32_t steps);
+int gmg_mesh_get(gmg_handle h, int32_t which, double* out);
+int gmg_mesh_pattern(int64_t n, int64_t nf, const int32_t* faces, int32_t* indptr, int32_t* indices, int64_t* nnz);
+
 /* ---- multi-GPU: row-range domain decomposition over the GPUs of one box (new design: the
  * reference is single-process). One process per GPU, SPMD: every rank creates the
  * same solver, configures (rank, world), joins the NCCL communicator and then makes the SAME
