@@ -73,6 +73,7 @@ SIGNATURES = {
     "gmg_stage_system": (C.c_int, [_h, C.c_int64, _i32p, _i32p, _f64p, _f64p, C.c_int32]),
     "gmg_solve_staged": (C.c_int, [_h]),
     "gmg_fetch_solution": (C.c_int, [_h, _f64p]),
+    "gmg_direct_solve": (C.c_int, [_h, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_int32]),
     "gmg_residual": (C.c_int, [_h, C.c_int64, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_int32, C.c_int32, _f64p]),
     "gmg_dist_configure": (C.c_int, [_h, C.c_int32, C.c_int32, C.c_int64]),
     "gmg_dist_unique_id": (C.c_int, [C.c_void_p, C.c_int64, _i64p]),

@@ -5,9 +5,9 @@ class ``MultigridSolver`` with the same 22 positional constructor arguments and 
 methods, plus the enums ``Hierarchy``, ``Sampling`` and ``Weighting``. The reference's
 ``gravomg/core.py`` runs unmodified on top of this module.
 
-Only the V-cycle path (``solve``, ``residual``, hierarchy accessors, timing writers) is
-implemented; ``direct_solve``, ``construct_sig21_hierarchy`` and ``toggle_hierarchy`` to a
-non-default hierarchy raise ``NotImplementedError`` (out of scope).
+The V-cycle path (``solve``, ``residual``, hierarchy accessors, timing writers) and ``direct_solve`` are
+implemented; ``construct_sig21_hierarchy`` and ``toggle_hierarchy`` to a non-default hierarchy raise
+``NotImplementedError`` (out of scope).
 """
 from __future__ import annotations
 
@@ -115,7 +115,14 @@ class MultigridSolver:
             raise NotImplementedError("only Hierarchy.OURS exists in this implementation")
 
     def direct_solve(self, lhs, rhs, pardiso):
-        raise NotImplementedError("direct_solve (Eigen LLT / Pardiso baselines) is outside the accelerated V-cycle path")
+        """core.cpp:74-78. ``pardiso`` selects Intel MKL upstream (a no-op there when MKL is absent,
+        multigrid_solver.cpp:1325-1364); here both values run the device solver: dense Cholesky up to 16384
+        rows, beyond that conjugate gradients preconditioned with the V-cycle, run to the fp64 rounding floor."""
+        ap, ai, ad = _csr_arrays(lhs, self._n)
+        b = _dense_rhs(rhs, self._n)
+        x = np.empty_like(b)
+        check(self._h, lib.gmg_direct_solve(self._h, self._n, i32(ap), i32(ai), f64(ad), f64(b), f64(x), b.shape[1]))
+        return x
 
     # ------------------------------------------------------------------ the hot path
     def solve(self, lhs, rhs):

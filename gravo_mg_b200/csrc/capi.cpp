@@ -171,10 +171,16 @@ int gmg_set_option(gmg_handle h, const char* key, double value) {
         else if (k == "p2p") s.p2p = value != 0.0, hierarchy = true;
         else if (k == "p2p_fuse") s.p2p_fuse = value != 0.0, cycle = true;
         else if (k == "dist_shard_setup") s.dist_shard_setup = (int)value, hierarchy = true;
+        else if (k == "dist_window") s.dist_window = value != 0.0, hierarchy = true;
         else if (k == "dist_skip_exchange") s.dist_skip_exchange = value != 0.0, cycle = true;
         else if (k == "spgemm_plan") s.spgemm_plan = value != 0.0, hierarchy = true;
         else if (k == "coarse_dataflow") s.coarse_dataflow = value != 0.0, cycle = true;
         else if (k == "diff_form") s.diff_form = value != 0.0, hierarchy = true;
+        else if (k == "krylov_patience") s.krylov_patience = (int)value;
+        else if (k == "krylov") {
+            require(value == 0.0 || value == 1.0 || value == 2.0, "krylov must be 0 (cycle loop), 1 (CG preconditioned with the cycle) or 2 (plain CG)");
+            s.krylov = (int)value;
+        }
         else throw std::invalid_argument("unknown option: " + k);
         require(s.params.pre_iters >= 0 && s.params.post_iters >= 0 && s.params.pre_iters <= 16 && s.params.post_iters <= 16, "sweep counts must be 0..16");
         require(s.params.smoother == GMG_SMOOTHER_JACOBI || s.params.smoother == GMG_SMOOTHER_CHEBYSHEV, "unknown smoother");
@@ -228,10 +234,13 @@ int gmg_get_option(gmg_handle h, const char* key, double* value) {
         else if (k == "p2p") *value = s.p2p;
         else if (k == "p2p_fuse") *value = s.p2p_fuse;
         else if (k == "dist_shard_setup") *value = s.dist_shard_setup;
+        else if (k == "dist_window") *value = s.dist_window;
         else if (k == "dist_skip_exchange") *value = s.dist_skip_exchange;
         else if (k == "spgemm_plan") *value = s.spgemm_plan;
         else if (k == "coarse_dataflow") *value = s.coarse_dataflow;
         else if (k == "diff_form") *value = s.diff_form;
+        else if (k == "krylov") *value = s.krylov;
+        else if (k == "krylov_patience") *value = s.krylov_patience;
         else throw std::invalid_argument("unknown option: " + k);
     });
 }
@@ -347,6 +356,74 @@ int gmg_solve(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t* a
         e.stage_system(n, a_indptr, a_indices, a_data, rhs, K, false);
         e.solve_staged();
         e.fetch_solution(x_out);
+    });
+}
+
+// direct_solve (core.cpp:74-78 -> multigrid_solver.cpp:1287-1321: Eigen::SimplicialLLT of the whole system).
+// Up to 16384 rows the system is factorised on the device by the dense Cholesky of the coarsest level (a twin
+// handle without hierarchy). Beyond that there is no sparse factorisation on the device: the system is solved
+// to the fp64 rounding floor by conjugate gradients preconditioned with the V-cycle, until the residual stops
+// decreasing (at most 100 iterations) — the accuracy of a backward-stable factorisation, not its algorithm.
+int gmg_direct_solve(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t* a_indices, const double* a_data,
+                     const double* rhs, double* x_out, int32_t K) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(a_indptr && a_indices && a_data && rhs && x_out, "null argument");
+        SolverState& s = h->s;
+        require(n == s.n, "lhs has a different number of rows than the point set of the constructor");
+        auto& tm = s.solver_timing;
+        if (n <= 16384) {
+            if (!s.direct_helper) {
+                s.direct_helper.reset(new gmg_solver());
+                SolverState& d = s.direct_helper->s;
+                d.params = s.params;
+                d.params.dtype = GMG_DTYPE_F64, d.params.build_hierarchy = 0, d.params.max_iter = 1;
+                d.n = n;
+                d.mass_diag = s.mass_diag;
+                d.hier.dof.push_back(n);
+            }
+            SolverState& d = s.direct_helper->s;
+            d.params.stopping_criteria = s.params.stopping_criteria;
+            gmg::EngineBase& e = engine(s.direct_helper.get());
+            try {
+                e.stage_system(n, a_indptr, a_indices, a_data, rhs, K, false);
+                e.solve_staged();
+                e.fetch_solution(x_out);
+            } catch (const std::exception& ex) {
+                throw std::runtime_error(std::string("direct_solve: ") + ex.what());
+            }
+            tm["direct_factor"] = d.solver_timing["reduction"] + d.solver_timing["coarsest_solve"];
+            tm["direct_solve"] = d.solver_timing["cycles"];
+            tm["direct_residual"] = d.solver_timing["residue"];
+        } else {
+            require(!s.hier.U.empty(), "direct_solve of more than 16384 rows needs the hierarchy (it is solved iteratively to the rounding floor)");
+            const gmg_params saved = s.params;
+            const int saved_krylov = s.krylov, saved_patience = s.krylov_patience;
+            s.params.tolerance = 1e-14, s.params.max_iter = 100;
+            s.krylov = 1, s.krylov_patience = 3;
+            gmg::EngineBase& e = engine(h);
+            auto put_back = [&] { s.params = saved, s.krylov = saved_krylov, s.krylov_patience = saved_patience; };
+            try {
+                for (int k0 = 0; k0 < K; k0 += 4) {  // the conjugate-gradient wrapper takes up to 4 columns at a time
+                    const int kt = std::min(4, K - k0);
+                    std::vector<double> b((size_t)n * kt), x((size_t)n * kt);
+                    for (int64_t i = 0; i < n; ++i)
+                        for (int k = 0; k < kt; ++k) b[(size_t)i * kt + k] = rhs[(size_t)i * K + k0 + k];
+                    e.stage_system(n, a_indptr, a_indices, a_data, b.data(), kt, false);
+                    e.solve_staged();
+                    e.fetch_solution(x.data());
+                    for (int64_t i = 0; i < n; ++i)
+                        for (int k = 0; k < kt; ++k) x_out[(size_t)i * K + k0 + k] = x[(size_t)i * kt + k];
+                    tm["direct_residual"] = k0 == 0 ? tm["residue"] : std::max(tm["direct_residual"], tm["residue"]);
+                }
+            } catch (...) {
+                put_back();
+                throw;
+            }
+            put_back();
+            tm["direct_factor"] = tm["reduction"] + tm["coarsest_solve"];
+            tm["direct_solve"] = tm["cycles"];
+        }
     });
 }
 

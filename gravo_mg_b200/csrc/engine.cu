@@ -12,6 +12,7 @@
 #include "host_xfer.h"
 #include "mesh_assembly.h"
 #include "nccl_dl.h"
+#include "pcg_kernels.h"
 #include "peer_exchange.h"
 #include "solver.h"
 #include "sparse_kernels.h"
@@ -45,27 +46,83 @@ struct DevMat {
     bool diff = false;
     SpmvPlan plan;
 
+    // Multi-GPU: the finest level's operators are stored by ROW SEGMENTS — a rank holds only the rows it works on
+    // (its own range plus what its share of the Galerkin product reads; on a periodic mesh that is two or three
+    // disjoint row ranges). The entry arrays (indices, values, rowidx) hold the entries of the stored rows, segment
+    // after segment, and the device row pointer is REBASED onto that storage: indptr[r] is the offset of row r's
+    // first entry in the local arrays for a stored row; rows that are not stored are empty. Kernels, tile
+    // descriptors and product plans work from the row pointer, so they are the same as for a fully stored
+    // matrix; row indices (and so every vector) stay global. Segments start at multiples of 4 entries (the
+    // 16-byte alignment of the bulk copies); the padding is marked with column -1.
+    struct Segment {
+        int r0, r1;        // rows [r0, r1)
+        int64_t g0, l0;    // first entry in the caller's (global) arrays / in the local arrays
+        int64_t len;
+    };
+    std::vector<Segment> segs;
+    std::vector<int> indptr_local;   // host copy of the rebased row pointer (empty: the global one is used)
+    int64_t stored = 0;
+    int* colp() const { return indices.ptr; }
+    int* rowidxp() const { return rowidx.ptr; }
+    double* v64p() const { return v64.ptr; }
+    double* vdp() const { return vd.ptr; }
+    float* v32p() const { return v32.ptr; }
+    bool windowed() const { return !indptr_local.empty(); }
+    // row pointer the tile planner and the entry ranges of this matrix are taken from
+    const std::vector<int>& indptr_host(const HostCsr& m) const { return windowed() ? indptr_local : m.indptr; }
+
     const T* vals() const;
-    void upload_pattern(const HostCsr& m, cudaStream_t s) {
+    // rows: ascending, disjoint, non-adjacent row ranges to store (nullptr: every row)
+    void upload_pattern(const HostCsr& m, cudaStream_t s, const std::vector<std::pair<int64_t, int64_t>>* rows_kept = nullptr) {
         rows = (int)m.rows, cols = (int)m.cols, nnz = m.nnz();
-        indptr.upload(m.indptr, s, 8);
-        indices.upload(m.indices.data(), m.indices.size(), s, 8);
-        v64.ensure(nnz, 8);
-        GMG_CUDA(cudaMemsetAsync(v64.ptr, 0, (nnz + 8) * sizeof(double), s));
+        segs.clear(), indptr_local.clear();
+        if (rows_kept && !(rows_kept->size() == 1 && (*rows_kept)[0].first == 0 && (*rows_kept)[0].second == m.rows)) {
+            indptr_local.assign((size_t)rows + 1, 0);
+            int64_t off = 0;
+            size_t next = 0;
+            for (int r = 0; r < rows; ++r) {
+                const bool starts = next < rows_kept->size() && (*rows_kept)[next].first == r;
+                if (starts) {
+                    off = (off + 3) & ~(int64_t)3;
+                    const int r1 = (int)(*rows_kept)[next].second;
+                    segs.push_back({r, r1, (int64_t)m.indptr[r], off, (int64_t)m.indptr[r1] - m.indptr[r]});
+                    ++next;
+                }
+                indptr_local[r] = (int)off;
+                const bool kept = !segs.empty() && r < segs.back().r1;
+                if (kept) off += m.indptr[r + 1] - m.indptr[r];
+            }
+            indptr_local[rows] = (int)off;
+            stored = off;
+            indptr.upload(indptr_local, s, 8);
+            indices.ensure(stored, 8);
+            GMG_CUDA(cudaMemsetAsync(indices.ptr, 0xFF, (stored + 8) * sizeof(int), s));  // padding: column -1
+            for (const Segment& g : segs)
+                if (g.len) GMG_CUDA(cudaMemcpyAsync(indices.ptr + g.l0, m.indices.data() + g.g0, g.len * sizeof(int), cudaMemcpyHostToDevice, s));
+        } else {
+            segs.push_back({0, rows, 0, 0, nnz});
+            stored = nnz;
+            indptr.upload(m.indptr, s, 8);
+            indices.upload(m.indices.data(), m.indices.size(), s, 8);
+        }
+        v64.ensure(stored, 8);
+        GMG_CUDA(cudaMemsetAsync(v64.ptr, 0, (stored + 8) * sizeof(double), s));
         if (sizeof(T) == 4) {
-            v32.ensure(nnz, 8);
-            GMG_CUDA(cudaMemsetAsync(v32.ptr, 0, (nnz + 8) * sizeof(float), s));
+            v32.ensure(stored, 8);
+            GMG_CUDA(cudaMemsetAsync(v32.ptr, 0, (stored + 8) * sizeof(float), s));
         }
     }
-    void upload_values(const double* host, cudaStream_t s) {
-        if (nnz) GMG_CUDA(cudaMemcpyAsync(v64.ptr, host, nnz * sizeof(double), cudaMemcpyHostToDevice, s));
+    void upload_values(const double* host, cudaStream_t s) {  // host: the caller's (global) value array
+        for (const Segment& g : segs)
+            if (g.len) GMG_CUDA(cudaMemcpyAsync(v64.ptr + g.l0, host + g.g0, g.len * sizeof(double), cudaMemcpyHostToDevice, s));
     }
     void refresh_cast(cudaStream_t s) {
-        if (sizeof(T) == 4) launch_cast_f64_f32(v64.ptr, v32.ptr, (size_t)nnz, s);
+        if (sizeof(T) == 4) launch_cast_f64_f32(v64.ptr, v32.ptr, (size_t)stored, s);
     }
     void make_rowidx(cudaStream_t s) {
-        rowidx.ensure(std::max<int64_t>(nnz, 1));
-        launch_expand_rows(rows, indptr.ptr, rowidx.ptr, s);
+        rowidx.ensure(std::max<int64_t>(stored, 1));
+        GMG_CUDA(cudaMemsetAsync(rowidx.ptr, 0, std::max<int64_t>(stored, 1) * sizeof(int), s));  // padding entries: row 0
+        for (const Segment& g : segs) launch_expand_rows(g.r1, indptr.ptr, rowidx.ptr, s, g.r0);
     }
     // Choose the kernel path and build the row tiles for the staged one.
     // `early_rows` (multi-GPU, may be null): rows that are pushed to peers or gather halo entries;
@@ -115,8 +172,8 @@ struct DevMat {
         }
     }
 };
-template <> const double* DevMat<double>::vals() const { return v64.ptr; }
-template <> const float* DevMat<float>::vals() const { return v32.ptr; }
+template <> const double* DevMat<double>::vals() const { return v64p(); }
+template <> const float* DevMat<float>::vals() const { return v32p(); }
 
 struct ProfileSlot {
     double ms = 0.0;
@@ -140,8 +197,8 @@ public:
         GMG_CUDA(cudaMemsetAsync(ctl_.ptr, 0, 3 * sizeof(CycleControl), stream_));
         partials_.ensure(kNormChunkStride * kMaxNormChunks);
         rho_.ensure(kMaxLevels);
-        tail_bar_.ensure(4);
-        GMG_CUDA(cudaMemsetAsync(tail_bar_.ptr, 0, 4 * sizeof(unsigned), stream_));
+        tail_bar_.ensure(8);
+        GMG_CUDA(cudaMemsetAsync(tail_bar_.ptr, 0, 8 * sizeof(unsigned), stream_));
         weights_.ensure((size_t)kMaxLevels * 2 * kMaxSweeps);
         weights64_.ensure((size_t)kMaxLevels * 2 * kMaxSweeps);
         GMG_CUDA(cudaMallocHost((void**)&ctl_host_, sizeof(CycleControl)));
@@ -176,6 +233,7 @@ public:
     }
     void invalidate_cycle() override {
         cycle_dirty_ = true;
+        kry_ops_dirty_ = true;
         numeric_ready_ = false;  // the smoother dampings are part of the numeric setup
     }
 
@@ -202,13 +260,24 @@ public:
             // the usual repeated solve: same pattern, new values. Values and rhs stream to HBM through
             // pinned chunks while the same worker threads compare the pattern with the staged one.
             std::vector<HostTransfer::Copy> copies = value_copies(data, rhs, nnz, n, K);
-            std::vector<HostTransfer::Compare> compares(2);
+            // (multi-GPU, windowed storage: every rank checks the column indices of its own window; the ranks
+            // then agree, so a change anywhere re-stages everywhere)
+            const DevMat<T>& a0 = lv_[0].A;
+            std::vector<HostTransfer::Compare> compares(1);
             compares[0].a = st_->a_pat[0].indptr.data(), compares[0].b = indptr, compares[0].bytes = (size_t)(n + 1) * sizeof(int);
-            compares[1].a = st_->a_pat[0].indices.data(), compares[1].b = indices, compares[1].bytes = (size_t)nnz * sizeof(int);
+            for (const auto& g : a0.segs) {
+                HostTransfer::Compare c;
+                c.a = st_->a_pat[0].indices.data() + g.g0, c.b = indices + g.g0, c.bytes = (size_t)g.len * sizeof(int);
+                compares.push_back(c);
+            }
             same = xf->upload_and_compare(copies, compares, stream_);
+            if (a0.windowed()) same = all_ranks_agree(same);
         } else if (same_shape) {
-            same = std::memcmp(st_->a_pat[0].indptr.data(), indptr, (n + 1) * sizeof(int)) == 0 &&
-                   std::memcmp(st_->a_pat[0].indices.data(), indices, nnz * sizeof(int)) == 0;
+            const DevMat<T>& a0 = lv_[0].A;
+            same = std::memcmp(st_->a_pat[0].indptr.data(), indptr, (n + 1) * sizeof(int)) == 0;
+            for (const auto& g : a0.segs)
+                same = same && std::memcmp(st_->a_pat[0].indices.data() + g.g0, indices + g.g0, g.len * sizeof(int)) == 0;
+            if (a0.windowed()) same = all_ranks_agree(same);
         }
         const bool uploaded = same && xf;
         if (!same) {
@@ -226,7 +295,9 @@ public:
                 xf->upload_and_compare(value_copies(data, rhs, nnz, n, K), {}, stream_);
             } else {
                 lv_[0].A.upload_values(data, stream_);
-                GMG_CUDA(cudaMemcpyAsync(rhs64_.ptr, rhs, (size_t)n * K * sizeof(double), cudaMemcpyHostToDevice, stream_));
+                for (const auto& rr : rhs_rows_)
+                    GMG_CUDA(cudaMemcpyAsync(rhs64_.ptr + (size_t)rr.first * K, rhs + (size_t)rr.first * K,
+                                             (size_t)(rr.second - rr.first) * K * sizeof(double), cudaMemcpyHostToDevice, stream_));
             }
         }
         numeric_ready_ = false;
@@ -243,17 +314,42 @@ public:
         auto& tt = st_->transfer_timing;
         tt["stage_host_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         tt["pattern_reused"] = same ? 1.0 : 0.0;
-        tt["h2d_bytes"] = (double)((size_t)nnz * sizeof(double) + (size_t)n * K * sizeof(double) +
-                                   (same ? 0 : (size_t)(n + 1 + nnz) * sizeof(int)));
+        size_t value_entries = 0, rhs_rows = 0;
+        for (const auto& g : lv_[0].A.segs) value_entries += (size_t)g.len;
+        for (const auto& rr : rhs_rows_) rhs_rows += (size_t)(rr.second - rr.first);
+        tt["h2d_bytes"] = (double)(value_entries * sizeof(double) + rhs_rows * K * sizeof(double) +
+                                   (same ? 0 : (size_t)(n + 1 + value_entries) * sizeof(int)));
         tt["transfer_threads"] = xf ? (double)xf->threads() : 0.0;
     }
 
+    // Multi-GPU: true only when `mine` is true on every rank (NCCL min over one int; one host synchronisation).
+    bool all_ranks_agree(bool mine) {
+        if (st_->dist.world <= 1 || !comm_) return mine;
+        flag_dev_.ensure(1);
+        int v = mine ? 1 : 0;
+        GMG_CUDA(cudaMemcpyAsync(flag_dev_.ptr, &v, sizeof v, cudaMemcpyHostToDevice, stream_));
+        GMG_NCCL(nccl().AllReduce(flag_dev_.ptr, flag_dev_.ptr, 1, ncclInt, ncclMin, comm_, stream_));
+        GMG_CUDA(cudaMemcpyAsync(&v, flag_dev_.ptr, sizeof v, cudaMemcpyDeviceToHost, stream_));
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+        return v != 0;
+    }
+
     std::vector<HostTransfer::Copy> value_copies(const double* data, const double* rhs, int64_t nnz, int64_t n, int K) {
-        std::vector<HostTransfer::Copy> c(2);
-        c[0].dev = lv_[0].A.v64.ptr, c[0].host = data, c[0].bytes = (size_t)nnz * sizeof(double);
+        std::vector<HostTransfer::Copy> c;
+        // the matrix values this rank stores (multi-GPU: the row segments of the finest level it works on)
+        for (const auto& g : lv_[0].A.segs) {
+            HostTransfer::Copy cp;
+            cp.dev = lv_[0].A.v64.ptr + g.l0, cp.host = data + g.g0, cp.bytes = (size_t)g.len * sizeof(double);
+            c.push_back(cp);
+        }
         // the right-hand side is not needed before the cycles start: it travels on a second stream so
         // the Galerkin reduction and the coarse factor begin as soon as the matrix values have arrived
-        c[1].dev = rhs64_.ptr, c[1].host = rhs, c[1].bytes = (size_t)n * K * sizeof(double), c[1].stream = stream2_;
+        for (const auto& rr : rhs_rows_) {
+            HostTransfer::Copy cp;
+            cp.dev = rhs64_.ptr + (size_t)rr.first * K, cp.host = rhs + (size_t)rr.first * K;
+            cp.bytes = (size_t)(rr.second - rr.first) * K * sizeof(double), cp.stream = stream2_;
+            c.push_back(cp);
+        }
         return c;
     }
 
@@ -329,7 +425,7 @@ public:
         GMG_CUDA(cudaSetDevice(st_->params.device));
         require_mesh(true);
         mesh_.face_geometry(mesh_pos_.ptr, MESH_MASS_BARYCENTRIC, stream_);
-        mesh_.stiffness(lv_[0].A.indptr.ptr, lv_[0].A.indices.ptr, mesh_s_.ptr, stream_);
+        mesh_.stiffness(lv_[0].A.indptr.ptr, lv_[0].A.colp(), mesh_s_.ptr, stream_);
         mesh_has_s_ = true;
     }
 
@@ -355,7 +451,7 @@ public:
             mesh_y_.upload(y, (size_t)st_->n * K, stream_);
             yd = mesh_y_.ptr;
         }
-        mesh_.system(lv_[0].A.indptr.ptr, lv_[0].A.indices.ptr, alpha, beta, mesh_s_.ptr, mesh_m_.ptr, yd, K, lv_[0].A.v64.ptr,
+        mesh_.system(lv_[0].A.indptr.ptr, lv_[0].A.colp(), alpha, beta, mesh_s_.ptr, mesh_m_.ptr, yd, K, lv_[0].A.v64p(),
                      rhs64_.ptr, stream_);
         if (y) GMG_CUDA(cudaStreamSynchronize(stream_));  // the caller's buffer has been read
         mark_staged_on_device();
@@ -435,6 +531,11 @@ public:
             hist_ms_.ensure(p.max_iter);
         }
         if (cycle_dirty_) build_cycle();
+        if (st_->krylov) {
+            solve_staged_krylov();
+            return;
+        }
+        x_final_ = x_final_cycle_;
         int64_t launches = 0;
 
         GMG_CUDA(cudaMemsetAsync(ctl_.ptr, 0, sizeof(CycleControl), stream_));
@@ -514,6 +615,169 @@ public:
         if (ctl_host_->error & 2) throw std::runtime_error("residual became non-finite (diverged); try a smaller omega");
     }
 
+    // ------------------------------------------------------------------ conjugate gradients around the cycle
+    // Option krylov = 1: preconditioned CG with ONE cycle (V, F or W; zero initial guess; the post-smoothing runs
+    // the pre-smoothing dampings in reverse, so the cycle is a symmetric operator) as the preconditioner;
+    // krylov = 2: plain CG (the reference's solverType 4, multigrid_solver.cpp:1453-1477). Same stopping rule,
+    // timing keys and convergence trace as the cycle loop: one iteration = one cycle + one product with A.
+    // The residual is carried by the recurrence r -= alpha A p; when it meets the tolerance the true residual
+    // b - A x is evaluated, and the iteration restarts from it if rounding has let the two drift apart.
+    void solve_staged_krylov() {
+        const gmg_params& p = st_->params;
+        if (sizeof(T) != 8) throw std::invalid_argument("the conjugate-gradient wrapper needs dtype float64");
+        if (st_->dist.world > 1) throw std::invalid_argument("the conjugate-gradient wrapper is single-GPU for now");
+        if (K_ > kPcgMaxK) throw std::invalid_argument("the conjugate-gradient wrapper handles 1..4 right-hand sides");
+        if (n_levels_ == 0 && st_->krylov == 1) throw std::invalid_argument("no hierarchy to precondition with (N <= lower_bound): use the plain solve");
+        const bool precond = st_->krylov == 1;
+        const int n = lv_[0].n;
+        const size_t count = (size_t)n * K_;
+        double* xk = reinterpret_cast<double*>(kry_x_.ptr);
+        if (kry_x_.count < count) kry_x_.ensure(count), kry_p_.ensure(count), kry_q_.ensure(count), xk = kry_x_.ptr;
+        kry_sc_.ensure(1), kry_part_.ensure((size_t)kPcgBlocks * 2 * kPcgMaxK);
+        if (kry_ops_dirty_ || kry_K_ != K_) build_krylov_cycle();
+        double* r = reinterpret_cast<double*>(lv_[0].b.ptr);   // the residual is the right-hand side of the preconditioning cycle
+        double* z = precond ? reinterpret_cast<double*>(kry_z_) : r;
+        const double* w = p.stopping_criteria == 2 ? mass_.ptr : p.stopping_criteria == 1 ? minv_.ptr : nullptr;
+        int64_t launches = 0;
+
+        GMG_CUDA(cudaMemsetAsync(ctl_.ptr, 0, sizeof(CycleControl), stream_));
+        GMG_CUDA(cudaEventRecord(ev_[0], stream_));
+        launches += setup_numeric(ev_[1]);
+        if (rhs_pending_) {
+            GMG_CUDA(cudaStreamWaitEvent(stream_, rhs_ready_, 0));
+            rhs_pending_ = false;
+        }
+        GMG_CUDA(cudaEventRecord(ev_[2], stream_));
+        launch_cycle_begin(ctl_.ptr, p.max_iter, p.stopping_criteria, p.tolerance, K_, stream_);
+        // x0 = rhs (core.cpp:69)
+        GMG_CUDA(cudaMemcpyAsync(xk, rhs64_.ptr, count * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+        NormChunks chunks;
+        chunks.n_chunks = 1, chunks.kt[0] = K_;
+        auto true_residual = [&](bool also_r) {  // r = b - A x (also_r) and its norm partials
+            SpmvArgs<T> a = base_args(lv_[0].A);
+            a.x = reinterpret_cast<const T*>(xk), a.b = reinterpret_cast<const T*>(rhs64_.ptr), a.out = reinterpret_cast<T*>(r);
+            a.weight = w, a.partials = partials_.ptr;
+            chunks.n_blocks[0] = launch_spmv<T>(also_r ? EPI_RESNORM : EPI_NORM, K_, a, lv_[0].A.plan, stream_);
+            ++launches;
+        };
+        auto restart = [&] {  // direction state cleared: the next iteration is a steepest-descent step from r
+            GMG_CUDA(cudaMemsetAsync(kry_sc_.ptr, 0, sizeof(PcgScalars), stream_));
+            GMG_CUDA(cudaMemsetAsync(kry_p_.ptr, 0, count * sizeof(double), stream_));
+            GMG_CUDA(cudaMemsetAsync(kry_q_.ptr, 0, count * sizeof(double), stream_));
+            true_residual(true);
+            if (precond)  // first smoothing sweep of the cycle from a zero guess: z0 = omega D^-1 r (alpha = 0: x, r unchanged)
+                launch_pcg_update(n, K_, xk, r, kry_p_.ptr, kry_q_.ptr, rhs64_.ptr, w, reinterpret_cast<const double*>(lv_[0].dinv.ptr),
+                                  weights64_.ptr, reinterpret_cast<double*>(kry_z0_), kry_sc_.ptr, kry_part_.ptr, stream_), ++launches;
+        };
+        restart();
+        int restarts = 0, stale = 0;
+        double best = 1.7976931348623157e308;
+        bool done = false;
+        while (!done) {
+            // ---- one iteration: z = M^-1 r, beta, p, q = A p, alpha, x / r update, stopping test
+            if (precond)
+                for (const Op& op : kry_ops_) launches += run_op(op, stream_, 0);
+            launch_pcg_dot(0, n, K_, r, z, kry_part_.ptr, tail_bar_.ptr + 4, kry_sc_.ptr, stream_);
+            launch_pcg_direction(n, K_, z, kry_p_.ptr, kry_sc_.ptr, stream_);
+            {
+                SpmvArgs<T> a = base_args(lv_[0].A);  // q = A p, cancellation-free form where the level has it
+                a.x = reinterpret_cast<const T*>(kry_p_.ptr), a.out = reinterpret_cast<T*>(kry_q_.ptr);
+                launch_spmv<T>(EPI_SPMV, K_, a, lv_[0].A.plan, stream_);
+            }
+            launch_pcg_dot(1, n, K_, kry_p_.ptr, kry_q_.ptr, kry_part_.ptr, tail_bar_.ptr + 4, kry_sc_.ptr, stream_);
+            chunks.n_blocks[0] = launch_pcg_update(n, K_, xk, r, kry_p_.ptr, kry_q_.ptr, rhs64_.ptr, w, reinterpret_cast<const double*>(lv_[0].dinv.ptr),
+                                                   weights64_.ptr, precond ? reinterpret_cast<double*>(kry_z0_) : nullptr, kry_sc_.ptr, partials_.ptr, stream_);
+            launch_norm_finalize(partials_.ptr, chunks, ctl_.ptr, hist_res_.ptr, hist_ms_.ptr, 1, 0, stream_);
+            launches += 6;
+            GMG_CUDA(cudaMemcpyAsync(ctl_host_, ctl_.ptr, sizeof(CycleControl), cudaMemcpyDeviceToHost, stream_));
+            GMG_CUDA(cudaStreamSynchronize(stream_));
+            if (ctl_host_->error) break;
+            if (st_->krylov_patience > 0 && !ctl_host_->done) {  // run to the rounding floor: stop once the residual stagnates
+                stale = ctl_host_->residue < 0.98 * best ? 0 : stale + 1;
+                best = std::min(best, ctl_host_->residue);
+                if (stale >= st_->krylov_patience) break;
+            }
+            if (!ctl_host_->done) continue;
+            done = true;
+            if (ctl_host_->residue <= p.tolerance) {
+                // met by the recurrence: judge the true residual, carry on from it if it is not there yet
+                true_residual(false);
+                launch_norm_finalize(partials_.ptr, chunks, ctl_.ptr, nullptr, nullptr, 0, 0, stream_);
+                ++launches;
+                GMG_CUDA(cudaMemcpyAsync(ctl_host_, ctl_.ptr, sizeof(CycleControl), cudaMemcpyDeviceToHost, stream_));
+                GMG_CUDA(cudaStreamSynchronize(stream_));
+                if (ctl_host_->residue > p.tolerance && ctl_host_->iter < p.max_iter && restarts < 3) {
+                    ++restarts;
+                    GMG_CUDA(cudaMemsetAsync(&ctl_.ptr->done, 0, sizeof(int), stream_));
+                    restart();
+                    done = false;
+                }
+            }
+        }
+        GMG_CUDA(cudaEventRecord(ev_[3], stream_));
+        GMG_CUDA(cudaStreamSynchronize(stream_));
+        x_final_ = reinterpret_cast<T*>(xk);
+        const int iters = ctl_host_->iter;
+        st_->last_launches = launches;
+        std::vector<double> res(std::max(iters, 1)), ms(std::max(iters, 1));
+        if (iters > 0) {
+            GMG_CUDA(cudaMemcpy(res.data(), hist_res_.ptr, iters * sizeof(double), cudaMemcpyDeviceToHost));
+            GMG_CUDA(cudaMemcpy(ms.data(), hist_ms_.ptr, iters * sizeof(double), cudaMemcpyDeviceToHost));
+        }
+        st_->convergence.clear();
+        for (int i = 0; i < iters; ++i) st_->convergence.emplace_back(ms[i], res[i]);
+        float t01 = 0, t12 = 0, t23 = 0, t03 = 0;
+        GMG_CUDA(cudaEventElapsedTime(&t01, ev_[0], ev_[1]));
+        GMG_CUDA(cudaEventElapsedTime(&t12, ev_[1], ev_[2]));
+        GMG_CUDA(cudaEventElapsedTime(&t23, ev_[2], ev_[3]));
+        GMG_CUDA(cudaEventElapsedTime(&t03, ev_[0], ev_[3]));
+        auto& tm = st_->solver_timing;
+        tm["reduction"] = t01, tm["coarsest_solve"] = t12, tm["cycles"] = t23, tm["solver_total"] = t03;
+        tm["iterations"] = (double)iters, tm["residue"] = ctl_host_->residue;
+        st_->transfer_timing["krylov_restarts"] = restarts;
+        solved_ = true;
+        if (ctl_host_->error & 1) throw std::runtime_error("an operator has a missing, non-positive or non-finite diagonal entry (Jacobi smoother needs A_ii > 0)");
+        if (ctl_host_->error & 4) throw std::runtime_error("coarsest-level Cholesky broke down: the Galerkin operator is not positive definite");
+        if (ctl_host_->error & 2) throw std::runtime_error("residual became non-finite (diverged)");
+    }
+
+    // The preconditioning cycle: eps = cycle(A, r) from a zero guess, the residual in lv_[0].b; its first
+    // pre-smoothing sweep is written by the update kernel of the CG iteration (kry_z0_), its result is kry_z_.
+    void build_krylov_cycle() {
+        const gmg_params& p = st_->params;
+        std::vector<Op> saved;
+        saved.swap(ops_);
+        const int tail_level = tail_level_;
+        tail_level_ = -1;
+        T* cur = lv_[0].x.ptr;
+        T* alt = lv_[0].t.ptr;
+        kry_z0_ = cur;
+        if (n_levels_ > 0) {
+            const int pre_done = p.pre_iters >= 1 ? 1 : 0;
+            if (!pre_done) {
+                Op z;
+                z.kind = OP_ZERO, z.level = 0, z.zero_ptr = cur, z.zero_bytes = (size_t)lv_[0].n * K_ * sizeof(T);
+                ops_.push_back(z);
+            }
+            push_vcycle(0, cur, alt, pre_done, false, p.cycle_type);
+        }
+        kry_z_ = cur;
+        kry_ops_.swap(ops_);
+        ops_.swap(saved);
+        tail_level_ = tail_level;
+        kry_ops_dirty_ = false;
+        kry_K_ = K_;
+        set_launch_dry_run(true);
+        try {
+            for (const Op& op : kry_ops_)
+                if (op.plan) run_op(op, stream_, 0);
+        } catch (...) {
+            set_launch_dry_run(false);
+            throw;
+        }
+        set_launch_dry_run(false);
+    }
+
     // ------------------------------------------------------------------ residualCheck
     double residual(int64_t n, const int* indptr, const int* indices, const double* data, const double* rhs,
                     const double* x, int K, int type) override {
@@ -568,8 +832,12 @@ public:
         int64_t launches = 0;
         GMG_CUDA(cudaMemsetAsync(rho_.ptr, 0, kMaxLevels * sizeof(double), stream_));
         if (L > 0) {
-            launch_extract_dinv<T>(lv_[0].n, lv_[0].A.indptr.ptr, lv_[0].A.indices.ptr, lv_[0].A.v64.ptr, lv_[0].dinv.ptr,
-                                   rho_.ptr, ctl_.ptr, stream_, lv_[0].A.diff ? lv_[0].A.vd.ptr : nullptr);
+            // windowed storage (multi-GPU): every rank sees its own rows only; the Gershgorin bound is their maximum
+            const DevMat<T>& a0 = lv_[0].A;
+            const bool win = a0.windowed();
+            launch_extract_dinv<T>(win ? (int)st_->dist.end(0) : lv_[0].n, a0.indptr.ptr, a0.colp(), a0.v64p(), lv_[0].dinv.ptr, rho_.ptr,
+                                   ctl_.ptr, stream_, a0.diff ? a0.vdp() : nullptr, win ? (int)st_->dist.begin(0) : 0);
+            if (win) GMG_NCCL(nccl().AllReduce(rho_.ptr, rho_.ptr, 1, ncclDouble, ncclMax, comm_, stream_));
             ++launches;
         }
         lv_[0].A.refresh_cast(stream_);
@@ -579,28 +847,28 @@ public:
             Level& c = lv_[k + 1];
             const int64_t na = f.AP.e1 - f.AP.e0, nc = c.A.e1 - c.A.e0;
             if (f.AP.planned)
-                launch_spgemm_planned(na, f.AP.pair_off.ptr, f.AP.pairs.ptr, f.A.v64.ptr, f.P.v64.ptr, f.AP.v64.ptr + f.AP.e0, stream_);
+                launch_spgemm_planned(na, f.AP.pair_off.ptr, f.AP.pairs.ptr, f.A.v64p(), f.P.v64p(), f.AP.v64p() + f.AP.e0, stream_);
             else
-                launch_spgemm_numeric(na, f.AP.rowidx.ptr + f.AP.e0, f.AP.indices.ptr + f.AP.e0, f.AP.v64.ptr + f.AP.e0, f.A.indptr.ptr,
-                                      f.A.indices.ptr, f.A.v64.ptr, f.P.indptr.ptr, f.P.indices.ptr, f.P.v64.ptr, stream_);
+                launch_spgemm_numeric(na, f.AP.rowidxp() + f.AP.e0, f.AP.colp() + f.AP.e0, f.AP.v64p() + f.AP.e0, f.A.indptr.ptr,
+                                      f.A.colp(), f.A.v64p(), f.P.indptr.ptr, f.P.colp(), f.P.v64p(), stream_);
             if (c.A.planned)
-                launch_spgemm_planned(nc, c.A.pair_off.ptr, c.A.pairs.ptr, f.R.v64.ptr, f.AP.v64.ptr, c.A.v64.ptr + c.A.e0, stream_);
+                launch_spgemm_planned(nc, c.A.pair_off.ptr, c.A.pairs.ptr, f.R.v64p(), f.AP.v64p(), c.A.v64p() + c.A.e0, stream_);
             else
-                launch_spgemm_numeric(nc, c.A.rowidx.ptr + c.A.e0, c.A.indices.ptr + c.A.e0, c.A.v64.ptr + c.A.e0, f.R.indptr.ptr,
-                                      f.R.indices.ptr, f.R.v64.ptr, f.AP.indptr.ptr, f.AP.indices.ptr, f.AP.v64.ptr, stream_);
+                launch_spgemm_numeric(nc, c.A.rowidxp() + c.A.e0, c.A.colp() + c.A.e0, c.A.v64p() + c.A.e0, f.R.indptr.ptr,
+                                      f.R.colp(), f.R.v64p(), f.AP.indptr.ptr, f.AP.colp(), f.AP.v64p(), stream_);
             if (!c.A.share.empty()) {
                 // every rank computed the rows of its coarse range: all-gather the values of A_{k+1}
                 GMG_NCCL(nccl().GroupStart());
                 for (int q = 0; q < st_->dist.world; ++q) {
                     const size_t cnt = (size_t)(c.A.share[q + 1] - c.A.share[q]);
-                    double* at = c.A.v64.ptr + c.A.share[q];
+                    double* at = c.A.v64p() + c.A.share[q];
                     if (cnt) GMG_NCCL(nccl().Broadcast(at, at, cnt, ncclDouble, q, comm_, stream_));
                 }
                 GMG_NCCL(nccl().GroupEnd());
             }
             launches += 2;
             if (k + 1 < L) {
-                launch_extract_dinv<T>(c.n, c.A.indptr.ptr, c.A.indices.ptr, c.A.v64.ptr, c.dinv.ptr, rho_.ptr + k + 1, ctl_.ptr,
+                launch_extract_dinv<T>(c.n, c.A.indptr.ptr, c.A.colp(), c.A.v64p(), c.dinv.ptr, rho_.ptr + k + 1, ctl_.ptr,
                                        stream_);
                 c.A.refresh_cast(stream_);
                 launches += sizeof(T) == 4 ? 2 : 1;
@@ -613,7 +881,7 @@ public:
         }
         if (after_reduction) GMG_CUDA(cudaEventRecord(after_reduction, stream_));
         coarse_.set_dataflow(st_->coarse_dataflow);
-        coarse_.factor(lv_[L].A.indptr.ptr, lv_[L].A.indices.ptr, lv_[L].A.v64.ptr, ctl_.ptr, stream_, st_->profile);
+        coarse_.factor(lv_[L].A.indptr.ptr, lv_[L].A.colp(), lv_[L].A.v64p(), ctl_.ptr, stream_, st_->profile);
         launches += coarse_.launches_per_factor();
         numeric_ready_ = true;
         return launches;
@@ -809,6 +1077,7 @@ public:
         if (!pattern_ready_ || level < 0 || level > n_levels_) throw std::invalid_argument("no such level staged on the device");
         if (level > 0 && !numeric_ready_) throw std::logic_error("Galerkin operators exist after a solve or a level_op");
         const DevMat<T>& m = lv_[level].A;
+        if (m.windowed()) throw std::logic_error("this level is stored by row windows on a multi-GPU layout: no rank holds the whole operator");
         GMG_CUDA(cudaMemcpyAsync(indptr, m.indptr.ptr, ((size_t)m.rows + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream_));
         GMG_CUDA(cudaMemcpyAsync(indices, m.indices.ptr, (size_t)m.nnz * sizeof(int), cudaMemcpyDeviceToHost, stream_));
         GMG_CUDA(cudaMemcpyAsync(data, m.v64.ptr, (size_t)m.nnz * sizeof(double), cudaMemcpyDeviceToHost, stream_));
@@ -898,44 +1167,104 @@ private:
             }
             return mark;
         };
+        // multi-GPU: a sharded fine level computes only its share of the Galerkin product — the rows of A_{k+1} in
+        // this rank's coarse range and the rows [lo, hi) of A_k U_k those need (own fine range plus the rows its
+        // restriction gathers); the level operator is all-gathered per solve. On by default (option
+        // dist_shard_setup = 0: every rank computes whole products from whole operators).
+        const bool shard_setup = d.world > 1 && st_->dist_shard_setup != 0;
+        auto product_rows = [&](int k, int64_t& lo, int64_t& hi) {
+            const HostCsr& r = st_->r_host[k];
+            const int64_t cb = d.begin(k + 1), ce = d.end(k + 1);
+            lo = d.begin(k), hi = d.end(k);
+            for (int64_t I = cb; I < ce; ++I)
+                for (int q = r.indptr[I]; q < r.indptr[I + 1]; ++q) {
+                    lo = std::min<int64_t>(lo, r.indices[q]);
+                    hi = std::max<int64_t>(hi, (int64_t)r.indices[q] + 1);
+                }
+            if (ce <= cb) lo = hi = d.begin(k);
+        };
+        // ... and then the finest level is STORED by row segments too (DevMat): A_0 and A_0 U_0 the rows this rank's
+        // products read (own range + the rows its restriction gathers), U_0 the rows those products and the
+        // prolongation read, U_0^T this rank's coarse rows. HBM footprint and the per-solve upload of a rank are
+        // ~1/world of the system (option dist_window = 0: whole operators everywhere).
+        const bool window0 = shard_setup && st_->dist_window && n_levels_ > 0 && d.sharded(0);
+        typedef std::vector<std::pair<int64_t, int64_t>> RowRanges;
+        auto ranges_of = [](const std::vector<char>& mark) {  // marked rows as ranges; gaps of <= 256 rows are kept too
+            RowRanges out;
+            const int64_t n_rows = (int64_t)mark.size();
+            for (int64_t r = 0; r < n_rows;) {
+                if (!mark[r]) {
+                    ++r;
+                    continue;
+                }
+                int64_t e = r + 1;
+                while (e < n_rows && mark[e]) ++e;
+                if (!out.empty() && r - out.back().second <= 256)
+                    out.back().second = e;
+                else
+                    out.emplace_back(r, e);
+                r = e;
+            }
+            return out;
+        };
+        RowRanges a_rows, p_rows, c_rows;
+        rhs_rows_.assign(1, std::make_pair((int64_t)0, (int64_t)st_->n));
+        if (window0) {
+            const HostCsr& a0 = st_->a_pat[0];
+            const HostCsr& r0 = st_->r_host[0];
+            std::vector<char> ma((size_t)st_->n, 0), mp((size_t)st_->n, 0), mr((size_t)st_->n, 0);
+            for (int64_t r = d.begin(0); r < d.end(0); ++r) ma[r] = mp[r] = mr[r] = 1;
+            for (int64_t I = d.begin(1); I < d.end(1); ++I)
+                for (int q = r0.indptr[I]; q < r0.indptr[I + 1]; ++q) ma[r0.indices[q]] = 1;
+            a_rows = ranges_of(ma);
+            for (const auto& rr : a_rows)
+                for (int q = a0.indptr[rr.first]; q < a0.indptr[rr.second]; ++q) mp[a0.indices[q]] = 1;
+            p_rows = ranges_of(mp);
+            c_rows.assign(1, std::make_pair(d.begin(1), d.end(1)));
+            // x0 = rhs: this rank reads its own rows of b and x plus the entries of x its rows gather
+            for (const auto& list : d.halo[HALO_A][0].recv)
+                for (int c : list) mr[c] = 1;
+            rhs_rows_ = ranges_of(mr);
+        }
         int b = 0, e = -1;
         for (int k = 0; k < n_levels_; ++k) {
             const HostCsr& u = U[k];
             const HostCsr& r = st_->r_host[k];
-            lv_[k].P.upload_pattern(u, stream_);
+            const bool win = window0 && k == 0;
+            lv_[k].P.upload_pattern(u, stream_, win ? &p_rows : nullptr);
             lv_[k].P.upload_values(u.data.data(), stream_);
             lv_[k].P.refresh_cast(stream_);
             range(k, d.sharded(k), b, e);
             if (d.sharded(k)) {  // prolongation: rows of level k, gathers level k + 1, writes x_k (gathered through A_k)
                 const std::vector<char> early = early_rows(u, k, k + 1, {{HALO_A, k}});
-                lv_[k].P.make_plan(u.indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e, &early);
+                lv_[k].P.make_plan(lv_[k].P.indptr_host(u), st_->kernel_path, st_->staged_lanes, stream_, b, e, &early);
             } else
                 lv_[k].P.make_plan(u.indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e);
-            lv_[k].R.upload_pattern(r, stream_);
+            lv_[k].R.upload_pattern(r, stream_, win ? &c_rows : nullptr);
             lv_[k].R.upload_values(r.data.data(), stream_);
             lv_[k].R.refresh_cast(stream_);
             range(k + 1, d.sharded(k), b, e);  // rows of R are coarse points; sharded with the fine level
             const int lanes_r = st_->staged_lanes_r ? st_->staged_lanes_r : st_->staged_lanes;
             if (d.sharded(k)) {  // restriction: rows of level k + 1, gathers r_k, writes b_{k+1} and the first x_{k+1}
                 const std::vector<char> early = early_rows(r, k + 1, k, {{HALO_A, k + 1}});
-                lv_[k].R.make_plan(r.indptr, st_->kernel_path, lanes_r, stream_, b, e, &early);
+                lv_[k].R.make_plan(lv_[k].R.indptr_host(r), st_->kernel_path, lanes_r, stream_, b, e, &early);
             } else
                 lv_[k].R.make_plan(r.indptr, st_->kernel_path, lanes_r, stream_, b, e);
-            lv_[k].AP.upload_pattern(st_->ap_pat[k], stream_);
+            lv_[k].AP.upload_pattern(st_->ap_pat[k], stream_, win ? &a_rows : nullptr);
             lv_[k].AP.make_rowidx(stream_);
         }
         for (int k = 0; k <= n_levels_; ++k) {
-            lv_[k].A.upload_pattern(st_->a_pat[k], stream_);
+            lv_[k].A.upload_pattern(st_->a_pat[k], stream_, window0 && k == 0 ? &a_rows : nullptr);
             if (k == 0 && n_levels_ > 0 && st_->diff_form) {
-                lv_[0].A.vd.ensure(lv_[0].A.nnz, 8);
-                GMG_CUDA(cudaMemsetAsync(lv_[0].A.vd.ptr, 0, (lv_[0].A.nnz + 8) * sizeof(double), stream_));
+                lv_[0].A.vd.ensure(lv_[0].A.stored, 8);
+                GMG_CUDA(cudaMemsetAsync(lv_[0].A.vd.ptr, 0, (lv_[0].A.stored + 8) * sizeof(double), stream_));
                 lv_[0].A.diff = true;
             }
             if (k > 0) lv_[k].A.make_rowidx(stream_);
             range(k, d.sharded(k), b, e);
             if (d.sharded(k)) {  // sweeps / residual / norm: write x_k (gathered through A_k, or U_{k-1}) or r_k (through R_k)
                 const std::vector<char> early = early_rows(st_->a_pat[k], k, k, {{HALO_A, k}, {HALO_R, k}, {HALO_P, k - 1}});
-                lv_[k].A.make_plan(st_->a_pat[k].indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e, &early);
+                lv_[k].A.make_plan(lv_[k].A.indptr_host(st_->a_pat[k]), st_->kernel_path, st_->staged_lanes, stream_, b, e, &early);
             } else
                 lv_[k].A.make_plan(st_->a_pat[k].indptr, st_->kernel_path, st_->staged_lanes, stream_, b, e);
             lv_[k].dinv.ensure(std::max(lv_[k].n, 1));
@@ -947,33 +1276,25 @@ private:
             Level& f = lv_[k];
             Level& c = lv_[k + 1];
             f.AP.planned = c.A.planned = false;
-            // multi-GPU: a sharded fine level computes only its share of the product — the rows of
-            // A_{k+1} in this rank's coarse range and the rows of A_k U_k those need (own fine range plus
-            // the rows its restriction gathers); the level operator is all-gathered per solve
             f.AP.e0 = 0, f.AP.e1 = f.AP.nnz, c.A.e0 = 0, c.A.e1 = c.A.nnz, c.A.share.clear();
-            if (d.sharded(k) && (st_->dist_shard_setup > 0 || (st_->dist_shard_setup < 0 && d.world >= 8))) {
-                const HostCsr& r = st_->r_host[k];
+            if (d.sharded(k) && shard_setup) {
                 const HostCsr& ap = st_->ap_pat[k];
                 const HostCsr& ac = st_->a_pat[k + 1];
                 const int64_t cb = d.begin(k + 1), ce = d.end(k + 1);
-                int64_t lo = d.begin(k), hi = d.end(k);
-                for (int64_t I = cb; I < ce; ++I)
-                    for (int q = r.indptr[I]; q < r.indptr[I + 1]; ++q) {
-                        lo = std::min<int64_t>(lo, r.indices[q]);
-                        hi = std::max<int64_t>(hi, (int64_t)r.indices[q] + 1);
-                    }
-                if (ce <= cb) lo = hi = d.begin(k);
+                int64_t lo = 0, hi = 0;
+                product_rows(k, lo, hi);
                 f.AP.e0 = ap.indptr[lo], f.AP.e1 = ap.indptr[hi];
+                if (f.AP.windowed()) f.AP.e0 = 0, f.AP.e1 = f.AP.stored;  // exactly the rows this rank needs are stored
                 c.A.e0 = ac.indptr[cb], c.A.e1 = ac.indptr[ce];
                 c.A.share.resize(d.world + 1);
                 for (int q = 0; q <= d.world; ++q) c.A.share[q] = ac.indptr[d.ranges[k + 1][q]];
             }
             if (!st_->spgemm_plan || plan_pairs > st_->spgemm_plan_max_pairs) continue;
-            plan_pairs += build_spgemm_plan(f.AP.e1 - f.AP.e0, f.AP.rowidx.ptr + f.AP.e0, f.AP.indices.ptr + f.AP.e0, f.A.indptr.ptr,
-                                            f.A.indices.ptr, f.P.indptr.ptr, f.P.indices.ptr, f.AP.pair_off, f.AP.pairs, stream_);
+            plan_pairs += build_spgemm_plan(f.AP.e1 - f.AP.e0, f.AP.rowidxp() + f.AP.e0, f.AP.colp() + f.AP.e0, f.A.indptr.ptr,
+                                            f.A.colp(), f.P.indptr.ptr, f.P.colp(), f.AP.pair_off, f.AP.pairs, stream_);
             f.AP.planned = true;
-            plan_pairs += build_spgemm_plan(c.A.e1 - c.A.e0, c.A.rowidx.ptr + c.A.e0, c.A.indices.ptr + c.A.e0, f.R.indptr.ptr,
-                                            f.R.indices.ptr, f.AP.indptr.ptr, f.AP.indices.ptr, c.A.pair_off, c.A.pairs, stream_);
+            plan_pairs += build_spgemm_plan(c.A.e1 - c.A.e0, c.A.rowidxp() + c.A.e0, c.A.colp() + c.A.e0, f.R.indptr.ptr,
+                                            f.R.colp(), f.AP.indptr.ptr, f.AP.colp(), c.A.pair_off, c.A.pairs, stream_);
             c.A.planned = true;
         }
         st_->transfer_timing["galerkin_plan_pairs"] = (double)plan_pairs;
@@ -1119,6 +1440,7 @@ private:
             }
         }
         rhs64_.ensure((size_t)st_->n * K_);
+        rhs64_.zero(stream_);  // multi-GPU: a rank uploads only the rows it reads
         if (max_halo_ && !use_p2p()) halo_send_.ensure(max_halo_ * K_), halo_recv_.ensure(max_halo_ * K_);
         if (sizeof(T) == 4) {
             r64_.ensure((size_t)st_->n * K_);
@@ -1265,8 +1587,8 @@ private:
         SpmvArgs<T> a;
         a.n_rows = m.rows;
         a.ld = K_;
-        a.rowptr = m.indptr.ptr, a.colidx = m.indices.ptr, a.vals = m.vals();
-        if (m.diff && sizeof(T) == 8) a.vals = reinterpret_cast<const T*>(m.vd.ptr), a.diff = 1;
+        a.rowptr = m.indptr.ptr, a.colidx = m.colp(), a.vals = m.vals();
+        if (m.diff && sizeof(T) == 8) a.vals = reinterpret_cast<const T*>(m.vdp()), a.diff = 1;
         a.l2_hint = st_->l2_hints ? m.l2_hint : 0;
         a.omega = (T)st_->params.omega;
         a.ctl = ctl_.ptr;
@@ -1428,7 +1750,7 @@ private:
             push_vcycle(0, cur, alt, 1, true, p.cycle_type);
         }
         if (tail_level_ > 0 && tail_end_ > tail_begin_) collapse_tail();
-        x_final_ = cur;
+        x_final_ = x_final_cycle_ = cur;
         if (n_levels_ > 0 && !refine()) push_halo(0, HALO_A, cur);
         if (!refine())
         {   // residualCheck(LHS, b, x, stoppingCriteria) (multigrid_solver.cpp:1413)
@@ -1634,8 +1956,8 @@ private:
                 plan.path = 1, plan.lanes = lv_[0].A.plan.lanes;
                 SpmvArgs<double> a;
                 a.n_rows = lv_[0].n, a.ld = K_;
-                a.rowptr = lv_[0].A.indptr.ptr, a.colidx = lv_[0].A.indices.ptr, a.vals = lv_[0].A.v64.ptr;
-                if (lv_[0].A.diff) a.vals = lv_[0].A.vd.ptr, a.diff = 1;
+                a.rowptr = lv_[0].A.indptr.ptr, a.colidx = lv_[0].A.colp(), a.vals = lv_[0].A.v64p();
+                if (lv_[0].A.diff) a.vals = lv_[0].A.vdp(), a.diff = 1;
                 a.weight = p.stopping_criteria == 2 ? mass_.ptr : p.stopping_criteria == 1 ? minv_.ptr : nullptr;
                 a.ctl = ctl_.ptr;
                 const bool test = op.level >= 0;
@@ -1847,6 +2169,15 @@ private:
     DeviceBuffer<T> weights_;
     DeviceBuffer<int> q_indptr_, q_indices_;
     DeviceBuffer<double> q_vals_, q_b_, q_x_, q_vd_, q_dinv_, q_rho_;
+    DeviceBuffer<double> kry_x_, kry_p_, kry_q_, kry_part_;   // conjugate-gradient wrapper (option krylov)
+    DeviceBuffer<PcgScalars> kry_sc_;
+    std::vector<Op> kry_ops_;
+    T* kry_z_ = nullptr;
+    T* kry_z0_ = nullptr;
+    bool kry_ops_dirty_ = true;
+    int kry_K_ = 0;
+    std::vector<std::pair<int64_t, int64_t>> rhs_rows_;   // row ranges of the right-hand side this rank uploads (all rows on a single GPU)
+    DeviceBuffer<int> flag_dev_;
     MeshAssembler mesh_;               // device-side operator assembly (mesh_assembly.h)
     DeviceBuffer<double> mesh_pos_, mesh_s_, mesh_m_, mesh_y_;
     bool mesh_has_pos_ = false, mesh_has_s_ = false, mesh_has_m_ = false;
@@ -1870,6 +2201,7 @@ private:
     DeviceBuffer<unsigned char> tail_table_;
     DeviceBuffer<unsigned> tail_bar_;
     T* x_final_ = nullptr;
+    T* x_final_cycle_ = nullptr;       // where the plain cycle loop leaves the iterate (x_final_ may point at the Krylov iterate)
     int launches_per_cycle_ = 0;
     cudaGraphExec_t cycle_exec_ = nullptr, while_exec_ = nullptr;
     std::vector<cudaEvent_t> prof_events_;

@@ -53,6 +53,20 @@ struct NeighArray {  // n x width, -1 padded
     int at(int64_t i, int j) const { return a[i * width + j]; }
 };
 
+// fn(lo, hi) on contiguous chunks of [0, n), one chunk per worker thread (results must not depend on the split).
+template <typename F>
+void parallel_chunks(int64_t n, int64_t min_chunk, F&& fn) {
+    const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)hierarchy_threads(), 16, n / std::max<int64_t>(min_chunk, 1) + 1}));
+    if (n_threads == 1) {
+        fn((int64_t)0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back([&, t] { fn(n * t / n_threads, n * (t + 1) / n_threads); });
+    fn((int64_t)0, n / n_threads);
+    for (auto& th : pool) th.join();
+}
+
 struct Clock {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     double ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
@@ -270,20 +284,34 @@ void build_hierarchy(const double* pos_in, int64_t n, const int* neigh_in, int k
 
         // -- coarse adjacency: clusters joined by a fine edge (ms.cpp:178-207)
         Clock t_neigh;
+        // (every cluster's neighbour set is sorted and made unique, so it does not depend on the order its fine
+        // edges are visited in: clusters are processed on worker threads from a members-by-cluster list)
         std::vector<std::vector<int>> adj(nc);
-        for (int64_t i = 0; i < nf; ++i) {
-            for (int j = 0; j < ng.width; ++j) {
-                const int q = ng.at(i, j);
-                if (q < 0) break;
-                if (nearest[i] != nearest[q]) adj[nearest[i]].push_back(nearest[q]);
+        std::vector<int64_t> member_ptr((size_t)nc + 1, 0);
+        for (int64_t i = 0; i < nf; ++i) ++member_ptr[(size_t)nearest[i] + 1];
+        for (int64_t c = 0; c < nc; ++c) member_ptr[c + 1] += member_ptr[c];
+        std::vector<int> members_of((size_t)nf);
+        {
+            std::vector<int64_t> at(member_ptr.begin(), member_ptr.end() - 1);
+            for (int64_t i = 0; i < nf; ++i) members_of[at[nearest[i]]++] = (int)i;
+        }
+        parallel_chunks(nc, 2048, [&](int64_t c_lo, int64_t c_hi) {
+            for (int64_t c = c_lo; c < c_hi; ++c) {
+                std::vector<int>& a = adj[c];
+                for (int64_t t = member_ptr[c]; t < member_ptr[c + 1]; ++t) {
+                    const int i = members_of[t];
+                    for (int j = 0; j < ng.width; ++j) {
+                        const int q = ng.at(i, j);
+                        if (q < 0) break;
+                        if (nearest[q] != c) a.push_back(nearest[q]);
+                    }
+                }
+                std::sort(a.begin(), a.end());
+                a.erase(std::unique(a.begin(), a.end()), a.end());
             }
-        }
+        });
         size_t widest = 0;
-        for (auto& a : adj) {
-            std::sort(a.begin(), a.end());
-            a.erase(std::unique(a.begin(), a.end()), a.end());
-            widest = std::max(widest, a.size());
-        }
+        for (const auto& a : adj) widest = std::max(widest, a.size());
         NeighArray ng_next;
         ng_next.n = nc;
         ng_next.width = (int)std::max<size_t>(widest, 1);
@@ -330,28 +358,45 @@ void build_hierarchy(const double* pos_in, int64_t n, const int* neigh_in, int k
 
         // -- candidate triangles from the Voronoi dual (ms.cpp:248-281)
         Clock t_tri;
+        // (the triangles a coarse point creates depend on nothing but the adjacency: they are listed per point on
+        // worker threads and numbered afterwards in point order, the order the sequential loop creates them in)
         std::vector<int> tris;
         std::vector<Vec3> tri_normals;
         std::vector<std::vector<int>> incident(nc);
-        for (int64_t c = 0; c < nc; ++c) {
-            const auto& a = adj[c];
-            for (size_t s = 0; s < a.size(); ++s) {
-                const int v2 = a[s];
-                if (v2 < c) continue;
-                for (size_t t = s + 1; t < a.size(); ++t) {
-                    const int v3 = a[t];
-                    if (v3 < c) continue;
-                    if (opt.check_voronoi && !std::binary_search(adj[v2].begin(), adj[v2].end(), v3)) continue;
-                    const int id = (int)tri_normals.size();
-                    tris.push_back((int)c);
-                    tris.push_back(v2);
-                    tris.push_back(v3);
-                    tri_normals.push_back(normalized(cross(coarse.at(v2) - coarse.at(c), coarse.at(v3) - coarse.at(c))));
-                    incident[c].push_back(id);
-                    incident[v2].push_back(id);
-                    incident[v3].push_back(id);
+        {
+            std::vector<std::vector<int>> pairs_of(nc);  // (v2, v3) of the triangles created by point c
+            parallel_chunks(nc, 2048, [&](int64_t c_lo, int64_t c_hi) {
+                for (int64_t c = c_lo; c < c_hi; ++c) {
+                    const auto& a = adj[c];
+                    for (size_t s2 = 0; s2 < a.size(); ++s2) {
+                        const int v2 = a[s2];
+                        if (v2 < c) continue;
+                        for (size_t t = s2 + 1; t < a.size(); ++t) {
+                            const int v3 = a[t];
+                            if (v3 < c) continue;
+                            if (opt.check_voronoi && !std::binary_search(adj[v2].begin(), adj[v2].end(), v3)) continue;
+                            pairs_of[c].push_back(v2);
+                            pairs_of[c].push_back(v3);
+                        }
+                    }
                 }
-            }
+            });
+            std::vector<int64_t> first((size_t)nc + 1, 0);
+            for (int64_t c = 0; c < nc; ++c) first[c + 1] = first[c] + (int64_t)pairs_of[c].size() / 2;
+            const int64_t n_tri = first[nc];
+            tris.resize(3 * (size_t)n_tri);
+            tri_normals.resize((size_t)n_tri);
+            parallel_chunks(nc, 2048, [&](int64_t c_lo, int64_t c_hi) {
+                for (int64_t c = c_lo; c < c_hi; ++c)
+                    for (size_t t = 0; t < pairs_of[c].size() / 2; ++t) {
+                        const int64_t id = first[c] + (int64_t)t;
+                        const int v2 = pairs_of[c][2 * t], v3 = pairs_of[c][2 * t + 1];
+                        tris[3 * id] = (int)c, tris[3 * id + 1] = v2, tris[3 * id + 2] = v3;
+                        tri_normals[id] = normalized(cross(coarse.at(v2) - coarse.at(c), coarse.at(v3) - coarse.at(c)));
+                    }
+            });
+            for (int64_t id = 0; id < n_tri; ++id)  // ascending triangle id per point, as the sequential loop leaves them
+                for (int v = 0; v < 3; ++v) incident[tris[3 * id + v]].push_back((int)id);
         }
         if (opt.debug) out.all_triangles.push_back(tris);
         tm["triangle_finding"] += t_tri.ms();

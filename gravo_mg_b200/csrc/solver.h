@@ -13,6 +13,8 @@
 #include "hierarchy.h"
 #include "host_sparse.h"
 
+struct gmg_solver;
+
 namespace gmg {
 
 class EngineBase {
@@ -67,9 +69,11 @@ struct SolverState {
     bool p2p = true;                 // multi-GPU: halos and norms through NVLink peer memory (peer_exchange.h);
                                      // false: pack / ncclSend / ncclRecv / unpack and ncclAllReduce
     int dist_shard_setup = -1;       // multi-GPU: sharded levels compute only their share of the Galerkin product and the
-                                     // values are all-gathered (NCCL). -1: from 8 ranks on, 0 replicated, 1 sharded. Measured
-                                     // reduction per solve, replicated -> sharded: 0.66 -> 0.76 ms at 2 ranks, 1.22 -> 1.43 ms
-                                     // at 4: the NCCL all-gathers of the level values cost more than the products save
+                                     // values are all-gathered (NCCL). -1 / 1: on, 0: every rank computes whole products. Measured
+                                     // reduction per solve, replicated -> sharded: 0.66 -> 0.76 ms at 2 ranks, 1.22 -> 1.43 ms at 4
+                                     // (the all-gathers cost more than the products save) — but only the sharded product lets a
+                                     // rank store and upload just its row window of the finest level (dist_window), which saves more
+    bool dist_window = true;         // multi-GPU: finest-level operators stored (and uploaded per solve) by row windows, ~1/world per rank
     bool dist_skip_exchange = false; // measurement only: drop the halo exchanges of the cycle (results are wrong)
     bool p2p_fuse = true;            // p2p: pushes fused into the producing kernels, waits into the consuming ones
     bool l2_hints = false;           // L2 eviction-priority hints on the operator slabs of the finest level (evict_last for
@@ -79,6 +83,11 @@ struct SolverState {
     bool fuse_norm = true;           // stopping test fused with the next cycle's first sweep
     bool use_pdl = true;             // programmatic dependent launch of the row-product kernels
     bool coarse_dataflow = true;     // coarse factor as one dataflow kernel (dense_factor.cuh) / one kernel per phase
+    int krylov_patience = 0;         // krylov: stop when the residual has not improved for this many iterations (0 = off);
+                                     // used by gmg_direct_solve to run to the fp64 rounding floor
+    std::shared_ptr<gmg_solver> direct_helper;  // hierarchy-free twin used by gmg_direct_solve for small systems
+    int krylov = 0;                  // 0: the reference's loop of cycles; 1: conjugate gradients preconditioned with one cycle;
+                                     // 2: plain conjugate gradients (the reference's solverType 4)
     bool diff_form = true;           // finest level: cancellation-free row product sum_{j != i} A_ij (x_j - x_i) + s_i x_i
                                      // (sparse_kernels.cuh, SpmvArgs::diff); false: plain sum_j A_ij x_j
     bool spgemm_plan = true;         // Galerkin products from index-pair lists built once per pattern

@@ -91,12 +91,12 @@ __global__ void unpack_kernel(T* __restrict__ v, const int* __restrict__ idx, in
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) extract_dinv_kernel(int n, const int* __restrict__ rowptr,
+__global__ void __launch_bounds__(256) extract_dinv_kernel(int row_begin, int n, const int* __restrict__ rowptr,
                                                           const int* __restrict__ colidx,
                                                           const double* __restrict__ vals, T* __restrict__ dinv,
                                                           double* __restrict__ rho, CycleControl* ctl,
                                                           double* __restrict__ vals_diff) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
     double bound = 0.0;
     if (i < n) {
         double d = 0.0, absum = 0.0;
@@ -174,8 +174,8 @@ __global__ void cast_f32_f64_kernel(const float* __restrict__ s, double* __restr
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = (double)s[i];
 }
 
-__global__ void expand_rows_kernel(int n_rows, const int* __restrict__ rowptr, int* __restrict__ rowidx) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void expand_rows_kernel(int row_begin, int n_rows, const int* __restrict__ rowptr, int* __restrict__ rowidx) {
+    const int r = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     for (int p = rowptr[r]; p < rowptr[r + 1]; ++p) rowidx[p] = r;
 }
@@ -455,13 +455,13 @@ void launch_cycle_begin(CycleControl* ctl, int max_iter, int criterion, double t
 
 template <typename T>
 void launch_extract_dinv(int n, const int* rowptr, const int* colidx, const double* vals, T* dinv, double* rho,
-                         CycleControl* ctl, cudaStream_t stream, double* vals_diff) {
-    if (n <= 0) return;
-    extract_dinv_kernel<T><<<(n + 255) / 256, 256, 0, stream>>>(n, rowptr, colidx, vals, dinv, rho, ctl, vals_diff);
+                         CycleControl* ctl, cudaStream_t stream, double* vals_diff, int row_begin) {
+    if (n <= row_begin) return;
+    extract_dinv_kernel<T><<<(n - row_begin + 255) / 256, 256, 0, stream>>>(row_begin, n, rowptr, colidx, vals, dinv, rho, ctl, vals_diff);
     GMG_CUDA(cudaGetLastError());
 }
-template void launch_extract_dinv<double>(int, const int*, const int*, const double*, double*, double*, CycleControl*, cudaStream_t, double*);
-template void launch_extract_dinv<float>(int, const int*, const int*, const double*, float*, double*, CycleControl*, cudaStream_t, double*);
+template void launch_extract_dinv<double>(int, const int*, const int*, const double*, double*, double*, CycleControl*, cudaStream_t, double*, int);
+template void launch_extract_dinv<float>(int, const int*, const int*, const double*, float*, double*, CycleControl*, cudaStream_t, double*, int);
 
 template <typename T>
 void launch_smoother_weights(const double* rho, int n_levels, int pre, int post, int smoother, double omega, double alpha,
@@ -490,9 +490,9 @@ void launch_add_f32_to_f64(const float* e, double* x, size_t n, cudaStream_t str
     add_f32_to_f64_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, stream>>>(e, x, n);
     GMG_CUDA(cudaGetLastError());
 }
-void launch_expand_rows(int n_rows, const int* rowptr, int* rowidx, cudaStream_t stream) {
-    if (n_rows <= 0) return;
-    expand_rows_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(n_rows, rowptr, rowidx);
+void launch_expand_rows(int n_rows, const int* rowptr, int* rowidx, cudaStream_t stream, int row_begin) {
+    if (n_rows <= row_begin) return;
+    expand_rows_kernel<<<(n_rows - row_begin + 255) / 256, 256, 0, stream>>>(row_begin, n_rows, rowptr, rowidx);
     GMG_CUDA(cudaGetLastError());
 }
 void launch_spgemm_numeric(int64_t nnz_c, const int* c_rowidx, const int* c_col, double* c_val, const int* a_ptr,

@@ -66,7 +66,7 @@ constexpr int kMaxSweeps = 16;        // pre / post sweeps per level the weight 
 // a copy of vals with the row sum (error-free TwoSum accumulation) in place of the diagonal entry.
 template <typename T>
 void launch_extract_dinv(int n, const int* rowptr, const int* colidx, const double* vals, T* dinv, double* rho,
-                         CycleControl* ctl, cudaStream_t stream, double* vals_diff = nullptr);
+                         CycleControl* ctl, cudaStream_t stream, double* vals_diff = nullptr, int row_begin = 0);  // rows [row_begin, n)
 // Jacobi dampings per level and sweep from rho[level]: weights[(level * 2 + post) * kMaxSweeps + sweep].
 template <typename T>
 void launch_smoother_weights(const double* rho, int n_levels, int pre, int post, int smoother, double omega, double alpha,
@@ -74,7 +74,7 @@ void launch_smoother_weights(const double* rho, int n_levels, int pre, int post,
 void launch_cast_f64_f32(const double* src, float* dst, size_t n, cudaStream_t stream);
 void launch_cast_f32_f64(const float* src, double* dst, size_t n, cudaStream_t stream);
 void launch_add_f32_to_f64(const float* e, double* x, size_t n, cudaStream_t stream);  // x += e
-void launch_expand_rows(int n_rows, const int* rowptr, int* rowidx, cudaStream_t stream);
+void launch_expand_rows(int n_rows, const int* rowptr, int* rowidx, cudaStream_t stream, int row_begin = 0);  // rows [row_begin, n_rows)
 // C = A * B on an existing sorted pattern of C, one thread per stored entry of C, products
 // added in the order of A's row (the order a row-wise CPU Gustavson pass uses).
 void launch_spgemm_numeric(int64_t nnz_c, const int* c_rowidx, const int* c_col, double* c_val, const int* a_ptr,

@@ -93,8 +93,11 @@ const char* gmg_last_error(gmg_handle h);
  * of the restriction operators), "l2_hints" (0/1 L2 eviction-priority hints on the finest operators),
  * "trace" (0/1 device timeline, gmg_get_trace); multi-GPU: "p2p" (1 halo rows through NVLink peer memory,
  * 0 NCCL send/recv), "p2p_fuse" (0/1 pushes and waits fused into the row-product kernels), "dist_graph",
- * "dist_shard_setup" (-1 auto, 0 replicated, 1 sharded Galerkin reduction), "dist_skip_exchange"
- * (measurement only). Unknown keys fail. */
+ * "dist_shard_setup" (-1 auto, 0 replicated, 1 sharded Galerkin reduction), "dist_window" (0/1 finest level
+ * stored and uploaded by per-rank row windows), "dist_skip_exchange" (measurement only), "diff_form" (0/1
+ * cancellation-free row product on the finest level), "krylov" (0 the reference's loop of cycles, 1 conjugate
+ * gradients preconditioned with one cycle, 2 plain conjugate gradients = the reference's solverType 4),
+ * "krylov_patience" (stop after this many iterations without improvement; 0 off). Unknown keys fail. */
 int gmg_set_option(gmg_handle h, const char* key, double value);
 int gmg_get_option(gmg_handle h, const char* key, double* value);
 
@@ -128,6 +131,14 @@ int gmg_stage_system(gmg_handle h, int64_t n, const int32_t* a_indptr, const int
                      const double* a_data, const double* rhs, int32_t K);
 int gmg_solve_staged(gmg_handle h);
 int gmg_fetch_solution(gmg_handle h, double* x_out);
+
+/* direct_solve (core.cpp:74-78 -> multigrid_solver.cpp:1287-1321, Eigen::SimplicialLLT of the whole system;
+ * writes solverTiming keys direct_factor, direct_solve, direct_residual). n <= 16384: dense Cholesky on the
+ * device (the coarsest-level solver applied to the whole system). Larger n: no sparse factorisation exists on
+ * the device; the system is solved to the fp64 rounding floor by conjugate gradients preconditioned with the
+ * V-cycle until the residual stops decreasing. */
+int gmg_direct_solve(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t* a_indices, const double* a_data,
+                     const double* rhs, double* x_out, int32_t K);
 
 /* residualCheck (core.cpp:132-134 -> multigrid_solver.cpp:1228-1277). type 0..3. */
 int gmg_residual(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t* a_indices, const double* a_data,

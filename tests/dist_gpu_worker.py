@@ -33,20 +33,43 @@ def main():
         # exchange variants: NVLink peer-memory pushes (default) under the host loop and inside the
         # device-side while-graph, and the NCCL send/recv path; all must give the single-GPU bits
         variants = {}
-        for vname, (p2p, fuse, loop_mode, shard_setup) in {"p2p_fused_while_graph": (1, 1, 1, 1), "p2p_fused_host_loop": (1, 1, 0, 1),
-                                                           "p2p_push_kernels": (1, 0, 1, 1), "nccl": (0, 0, 0, 1),
-                                                           "replicated_galerkin_setup": (1, 1, 1, 0)}.items():
+        # (the default comes last: the layout queries below read it)
+        full_bytes = lhs.data.nbytes + rhs.nbytes
+        for vname, (p2p, fuse, loop_mode, shard_setup, window) in {"p2p_fused_host_loop": (1, 1, 0, 1, 1),
+                                                                   "p2p_push_kernels": (1, 0, 1, 1, 1), "nccl": (0, 0, 0, 1, 1),
+                                                                   "replicated_galerkin_setup": (1, 1, 1, 0, 0),
+                                                                   "sharded_setup_whole_operators": (1, 1, 1, 1, 0),
+                                                                   "p2p_fused_while_graph": (1, 1, 1, 1, 1)}.items():
             sharded = gravomg.MultigridSolver(V, neigh, M, **kw)
             sharded.solver.set_option("lanes", 1)
             sharded.solver.set_option("p2p", p2p)
             sharded.solver.set_option("p2p_fuse", fuse)
             sharded.solver.set_option("loop_mode", loop_mode)
             sharded.solver.set_option("dist_shard_setup", shard_setup)
+            sharded.solver.set_option("dist_window", window)
             sharded.distribute(replicate_rows=replicate_rows)
             xs = sharded.solve(lhs, rhs)
             xs2 = sharded.solve(lhs, rhs)  # repeated solve on the staged pattern
             variants[vname] = bool(np.array_equal(x1, xs)) and bool(np.array_equal(xs, xs2)) and \
                 sharded.solver_timing["iterations"] == single.solver_timing["iterations"]
+            tt = sharded.solver.transfer_timing()
+            variants[vname] = variants[vname] and tt["pattern_reused"] == 1.0
+            if window:  # row windows: a rank uploads about 1 / world of the values (plus the rows its products read)
+                variants[vname] = variants[vname] and tt["h2d_bytes"] <= full_bytes * (1.0 / world + 0.15)
+            else:
+                variants[vname] = variants[vname] and tt["h2d_bytes"] == full_bytes
+            if vname == "p2p_fused_while_graph":
+                # a change of the pattern (same shape) on the staged solver is seen by every rank: re-staged, same result
+                lhs2 = lhs.copy()
+                lhs2.indices = lhs2.indices.copy()
+                r0 = lhs2.shape[0] // (4 * world)  # inside rank 0's window only
+                seg = slice(lhs2.indptr[r0], lhs2.indptr[r0 + 1])
+                lhs2.indices[seg] = lhs2.indices[seg][::-1]
+                lhs2.data[seg] = lhs2.data[seg][::-1]  # the same matrix, one row stored in another order
+                xs3 = sharded.solve(lhs2, rhs)
+                variants["pattern_change_seen_by_all_ranks"] = sharded.solver.transfer_timing()["pattern_reused"] == 0.0 and \
+                    float(np.abs(xs3 - xs).max()) <= 1e-9 * float(np.abs(xs).max())
+                xs = sharded.solve(lhs, rhs)
         if name == "two_sharded_levels":
             # the direct (non-TMA) kernels carry the same fused push / wait
             pair = []

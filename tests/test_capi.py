@@ -67,9 +67,9 @@ def test_python_surface_matches_the_reference_binding():
 def test_out_of_scope_entry_points_raise(ico_small):
     s = ico_small.solver
     with pytest.raises(NotImplementedError):
-        s.direct_solve(ico_small.lhs, ico_small.rhs)
-    with pytest.raises(NotImplementedError):
         s.construct_sig21_hierarchy(ico_small.F)
+    with pytest.raises(NotImplementedError):
+        s.solver.toggle_hierarchy(1)  # Hierarchy.SIG21
 
 
 def test_timing_csv_writers(ico_small, tmp_path):
@@ -111,7 +111,8 @@ def test_options_round_trip_without_a_device(ico_small):
             "smoother": 0, "cheb_alpha": 8.0, "use_graph": 0, "loop_mode": 0, "kernel_path": 1, "lanes": 4, "lanes_r": 8,
             "pdl": 0, "fuse_norm": 0, "fuse_stop": 0, "tail_rows": 1000, "profile": 1, "trace": 1, "xfer_threads": 3,
             "spgemm_plan": 0, "coarse_dataflow": 0, "fp32_refine": 0, "l2_hints": 1, "p2p": 0, "p2p_fuse": 0,
-            "dist_graph": 0, "dist_shard_setup": 1, "dist_skip_exchange": 1}
+            "dist_graph": 0, "dist_shard_setup": 1, "dist_skip_exchange": 1, "dist_window": 0, "diff_form": 0, "krylov": 1,
+            "krylov_patience": 3}
     for k, v in keys.items():
         b.set_option(k, v)
         assert b.get_option(k) == pytest.approx(v), k
@@ -119,3 +120,9 @@ def test_options_round_trip_without_a_device(ico_small):
         b.set_option("no_such_option", 1)
     with pytest.raises(RuntimeError):
         b.set_option("lanes", 3)
+    # a rejected value does not stay behind
+    assert b.get_option("lanes") == 4
+    for key, bad, good in (("pre_iters", 20, 3), ("cheb_alpha", 0.5, 8.0), ("max_iter", 0, 7), ("krylov", 5, 1)):
+        with pytest.raises(RuntimeError):
+            b.set_option(key, bad)
+        assert b.get_option(key) == pytest.approx(good), key
