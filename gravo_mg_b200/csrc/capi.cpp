@@ -154,6 +154,7 @@ int gmg_set_option(gmg_handle h, const char* key, double value) {
         else if (k == "cheb_alpha") s.params.cheb_alpha = value, cycle = true;
         else if (k == "lanes") s.staged_lanes = (int)value, hierarchy = true;
         else if (k == "lanes_r") s.staged_lanes_r = (int)value, hierarchy = true;
+        else if (k == "restrict_path") s.restrict_path = (int)value, hierarchy = true;
         else if (k == "cycle_type") s.params.cycle_type = (int)value, cycle = true;
         else if (k == "use_graph") s.use_graph = value != 0.0;
         else if (k == "loop_mode") s.loop_mode = (int)value;
@@ -217,6 +218,7 @@ int gmg_get_option(gmg_handle h, const char* key, double* value) {
         else if (k == "cheb_alpha") *value = s.params.cheb_alpha;
         else if (k == "lanes") *value = s.staged_lanes;
         else if (k == "lanes_r") *value = s.staged_lanes_r;
+        else if (k == "restrict_path") *value = s.restrict_path;
         else if (k == "cycle_type") *value = s.params.cycle_type;
         else if (k == "use_graph") *value = s.use_graph;
         else if (k == "loop_mode") *value = s.loop_mode;

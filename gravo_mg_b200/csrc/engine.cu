@@ -271,13 +271,13 @@ public:
                 compares.push_back(c);
             }
             same = xf->upload_and_compare(copies, compares, stream_);
-            if (a0.windowed()) same = all_ranks_agree(same);
+            if (window0_) same = all_ranks_agree(same);  // layout property: every rank takes this branch
         } else if (same_shape) {
             const DevMat<T>& a0 = lv_[0].A;
             same = std::memcmp(st_->a_pat[0].indptr.data(), indptr, (n + 1) * sizeof(int)) == 0;
             for (const auto& g : a0.segs)
                 same = same && std::memcmp(st_->a_pat[0].indices.data() + g.g0, indices + g.g0, g.len * sizeof(int)) == 0;
-            if (a0.windowed()) same = all_ranks_agree(same);
+            if (window0_) same = all_ranks_agree(same);  // layout property: every rank takes this branch
         }
         const bool uploaded = same && xf;
         if (!same) {
@@ -834,7 +834,7 @@ public:
         if (L > 0) {
             // windowed storage (multi-GPU): every rank sees its own rows only; the Gershgorin bound is their maximum
             const DevMat<T>& a0 = lv_[0].A;
-            const bool win = a0.windowed();
+            const bool win = window0_;  // a property of the layout, the same on every rank (it decides a collective)
             launch_extract_dinv<T>(win ? (int)st_->dist.end(0) : lv_[0].n, a0.indptr.ptr, a0.colp(), a0.v64p(), lv_[0].dinv.ptr, rho_.ptr,
                                    ctl_.ptr, stream_, a0.diff ? a0.vdp() : nullptr, win ? (int)st_->dist.begin(0) : 0);
             if (win) GMG_NCCL(nccl().AllReduce(rho_.ptr, rho_.ptr, 1, ncclDouble, ncclMax, comm_, stream_));
@@ -1188,6 +1188,7 @@ private:
         // prolongation read, U_0^T this rank's coarse rows. HBM footprint and the per-solve upload of a rank are
         // ~1/world of the system (option dist_window = 0: whole operators everywhere).
         const bool window0 = shard_setup && st_->dist_window && n_levels_ > 0 && d.sharded(0);
+        window0_ = window0;
         typedef std::vector<std::pair<int64_t, int64_t>> RowRanges;
         auto ranges_of = [](const std::vector<char>& mark) {  // marked rows as ranges; gaps of <= 256 rows are kept too
             RowRanges out;
@@ -1245,11 +1246,13 @@ private:
             lv_[k].R.refresh_cast(stream_);
             range(k + 1, d.sharded(k), b, e);  // rows of R are coarse points; sharded with the fine level
             const int lanes_r = st_->staged_lanes_r ? st_->staged_lanes_r : st_->staged_lanes;
+            const int path_r = st_->restrict_path >= 0 ? st_->restrict_path : st_->kernel_path;
             if (d.sharded(k)) {  // restriction: rows of level k + 1, gathers r_k, writes b_{k+1} and the first x_{k+1}
                 const std::vector<char> early = early_rows(r, k + 1, k, {{HALO_A, k + 1}});
-                lv_[k].R.make_plan(lv_[k].R.indptr_host(r), st_->kernel_path, lanes_r, stream_, b, e, &early);
+                lv_[k].R.make_plan(lv_[k].R.indptr_host(r), path_r, lanes_r, stream_, b, e, &early);
             } else
-                lv_[k].R.make_plan(r.indptr, st_->kernel_path, lanes_r, stream_, b, e);
+                lv_[k].R.make_plan(r.indptr, path_r, lanes_r, stream_, b, e);
+            if (lv_[k].R.plan.path == 1 && st_->staged_lanes_r) lv_[k].R.plan.lanes = st_->staged_lanes_r;
             lv_[k].AP.upload_pattern(st_->ap_pat[k], stream_, win ? &a_rows : nullptr);
             lv_[k].AP.make_rowidx(stream_);
         }
@@ -2176,6 +2179,7 @@ private:
     T* kry_z0_ = nullptr;
     bool kry_ops_dirty_ = true;
     int kry_K_ = 0;
+    bool window0_ = false;   // multi-GPU: finest level stored by row segments (decided from the layout: identical on all ranks)
     std::vector<std::pair<int64_t, int64_t>> rhs_rows_;   // row ranges of the right-hand side this rank uploads (all rows on a single GPU)
     DeviceBuffer<int> flag_dev_;
     MeshAssembler mesh_;               // device-side operator assembly (mesh_assembly.h)

@@ -58,6 +58,7 @@ struct SolverState {
     bool use_graph = true;
     int loop_mode = 1;               // 1 device while-graph (the whole cycle loop is one launch), 0 host loop (one sync per cycle)
     int kernel_path = 0;             // 0 staged (TMA) where it fits, 1 direct everywhere
+    int restrict_path = -1;          // kernel path of the restriction operators only (-1 = follow kernel_path)
     int staged_lanes_r = 0;          // the same for the restriction operators U^T only (0 = follow staged_lanes)
     int staged_lanes = 0;            // staged kernels: threads per row; 0 = from the mean row length
     bool profile = false;

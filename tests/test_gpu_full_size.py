@@ -1,7 +1,9 @@
-"""BASELINE.json configurations at their full sizes, checked through size-independent properties
-(the oracle needs minutes at these sizes): the returned x satisfies the stopping criterion when
-the residual is recomputed on the host in fp64, residual histories are monotone, the columns of
-a multi-column solve are independent, a repeated solve reuses the staged pattern.
+"""BASELINE.json configurations at their full sizes. Config 2 (1 M vertices) is compared with the
+oracle directly — its Jacobi variant walks the same cycles (P2: residual history, cycle count, iterate) and
+its Gauss-Seidel run is the reference algorithm (P3); the larger configs are checked through
+size-independent properties: the returned x satisfies the stopping criterion when the residual is
+recomputed on the host in fp64, residual histories are monotone, the columns of a multi-column solve
+are independent, a repeated solve reuses the staged pattern.
 
   config 2  1 000 000-vertex torus, Poisson lhs = 1e-6 M + S, fp64, K = 1, 5 levels (lower_bound 500)
   config 3  ~5 000 000-vertex torus (2236 x 2236), smoothing lhs = M + 1e-3 S, rhs = M V (K = 3), fp32 levels
@@ -44,6 +46,29 @@ def test_config2_poisson_1m_fp64():
     x2 = s.solve(lhs, rhs)  # staged pattern reused, same bits
     np.testing.assert_array_equal(x, x2)
     assert s.solver.transfer_timing()["pattern_reused"] == 1.0
+    # P2 at full size: the oracle running the device's own cycle (same dampings, same cancellation-free row
+    # product on the finest level) takes the same number of cycles through the same residuals
+    from oracle import oracle
+
+    U = s.prolongation_matrices
+    weights = {k: s.solver.smoother_weights(k)[1:] for k in range(len(U))}
+    oj = oracle.OracleSolver(M, U, tolerance=1e-6, smoother="jacobi", weights=weights, row_product="diff")
+    xj = oj.solve(lhs, rhs)
+    assert int(oj.solver_timing["iterations"]) == int(t["iterations"])
+    hist_o = [r for _, r in oj.convergence]
+    # summation order of the Galerkin products and of the norm differs: 1e-6 relative on the early residuals, the
+    # last ones sit within a factor of 3 of the rounding floor of this nearly singular system (~2e-7)
+    for a, b in zip(hist, hist_o):
+        assert abs(a - b) <= 1e-5 * b + 1e-7
+    d = lhs @ (x - xj)
+    assert np.sqrt((m[:, None] * d * d).sum()) <= 2.1e-6 * np.sqrt((m[:, None] * rhs * rhs).sum())
+    # P3: the reference algorithm (lexicographic Gauss-Seidel) on the same system
+    og = oracle.OracleSolver(M, U, tolerance=1e-6, smoother="gs")
+    og.solve(lhs, rhs)
+    assert og.solver_timing["residue"] <= 1e-6
+    print(f"\n[config 2] cycles to 1e-6: device {int(t['iterations'])}, oracle Jacobi {int(oj.solver_timing['iterations'])}, "
+          f"reference Gauss-Seidel {int(og.solver_timing['iterations'])}; final residue device {t['residue']:.3e}, "
+          f"oracle Jacobi {oj.solver_timing['residue']:.3e}, Gauss-Seidel {og.solver_timing['residue']:.3e}")
 
 
 def test_config3_smoothing_5m_fp32_k3():
@@ -58,7 +83,7 @@ def test_config3_smoothing_5m_fp32_k3():
     t = s.solver_timing
     m = M.diagonal()
     res = _mnorm_residual(lhs, rhs, x, m)  # judged in fp64 on the host
-    assert res <= 2e-4 and t["residue"] <= 1e-4, (res, t)
+    assert res <= 1e-4 * (1 + 1e-3) and t["residue"] <= 1e-4, (res, t)
     hist = [r for _, r in s.convergence]
     assert all(a > b for a, b in zip(hist, hist[1:]))
     # the three columns are independent solves: column 1 alone gives the same bits
@@ -79,15 +104,15 @@ def test_config5_repeated_solves_2m_fp64_k3():
     import gravomg
     from gravo_mg_b200 import synth, util
 
-    V, S, M, neigh = _build(1414)
+    V, F = synth.torus_grid(1414, 1414)
+    V, S, M, neigh = synth.mesh_operators(V, F)
     s = gravomg.MultigridSolver(V, neigh, M, tolerance=1e-4)
     Vt = V.copy()
     m = M.diagonal()
     iters = []
     for step in range(6):
-        # demos/conformal_flow.py:54-59: M_t = mass(V_t) (here: the lumped mass rescaled, same pattern),
-        # lhs = M_t + 0.01 S, rhs = M_t V_t, V_{t+1} = normalize_area(solve)
-        Mt = M * (1.0 + 0.05 * step)
+        # demos/conformal_flow.py:54-59: M_t = mass(V_t), lhs = M_t + 0.01 S, rhs = M_t V_t, V_{t+1} = normalize_area(solve)
+        Mt = synth.mass_barycentric(Vt, F)
         lhs = (Mt + 0.01 * S).tocsr()
         rhs = Mt @ Vt
         x = s.solve(lhs, rhs)
@@ -95,7 +120,7 @@ def test_config5_repeated_solves_2m_fp64_k3():
         assert _mnorm_residual(lhs, rhs, x, m) <= 1e-4
         if step:
             assert s.solver.transfer_timing()["pattern_reused"] == 1.0
-        Vt = x / np.sqrt((x * x).sum(1).mean())
+        Vt = util.normalize_area(x, F)
     fresh = gravomg.MultigridSolver(V, neigh, M, tolerance=1e-4)
     np.testing.assert_array_equal(fresh.solve(lhs, rhs), x)  # reuse changes nothing
     assert max(iters) <= 12

@@ -62,7 +62,8 @@ def test_direct_solve_small_system_is_a_dense_factorisation(ico_small):
     t = s.solver_timing
     assert t["direct_factor"] > 0 and t["direct_solve"] > 0 and t["direct_residual"] <= 1e-13
     x = s.direct_solve(p.lhs, p.rhs, pardiso=True)  # Poisson, nearly singular: backward error
-    assert np.abs(p.lhs @ x - p.rhs).max() <= 1e-9 * np.abs(p.rhs).max()
+    floor = np.finfo(float).eps * (abs(p.lhs) @ np.abs(x)).max()  # x carries a constant ~4e4: rounding floor of A x
+    assert np.abs(p.lhs @ x - p.rhs).max() <= 50 * floor
     assert s.solve(lhs, rhs).shape == rhs.shape  # the V-cycle path of the same handle is untouched
 
 
