@@ -11,7 +11,8 @@
   3  2236 x 2236 torus (5.0 M vertices), smoothing lhs = M + 1e-3 S, rhs = M V (K = 3), fp32
      levels with fp64 defect correction, tolerance 1e-4; per-level achieved GB/s table.
   4  4472 x 4472 jittered torus point cloud (20.0 M points), symmetrised 8-nearest-neighbour graph
-     Laplacian, M = I/N, Poisson, fp64, K = 1; --gpus 1/2/4/8 solve the SAME system (strong scaling).
+     Laplacian, M = I/N, Poisson, fp64, K = 1, tolerance 1e-4 (the reference's default; 1e-6 is below the fp64
+     rounding floor of this system); --gpus 1/2/4/8 solve the SAME system (strong scaling).
   5  1414 x 1414 torus (2.0 M vertices), conformal flow (demos/conformal_flow.py:54-59): 100 time
      steps of M_t = mass(V_t), lhs = M_t + 0.01 S, rhs = M_t V_t, V = normalize_area(solve), fp64,
      K = 3, tolerance 1e-4, hierarchy / symbolic setup / graphs reused. A step is one time step.
@@ -103,7 +104,10 @@ def build_problem(args, world):
         neigh = gravomg.util.neighbors_from_stiffness(L)
         lhs, rhs = synth.poisson_system(L, M)
         p.V, p.S, p.M, p.neigh, p.lhs, p.rhs = P, L, M, neigh, lhs, rhs
-        p.tol, p.lower_bound, p.scaling = args.tol if args.tol else 1e-6, args.lower_bound if args.lower_bound else 500, "strong"
+        # tolerance: the reference's default / the paper's operating point (core.py:10). With M = I/N and tau = 1e-6 the
+        # fp64 rounding floor of this 20 M-point system is ~1e-6 for the device path and 2e-6 for the reference's
+        # Gauss-Seidel (100 cycles each, measured: profiles/r2_bench_c4_n1_tol1e-6.json), so 1e-6 is not a usable target here
+        p.tol, p.lower_bound, p.scaling = args.tol if args.tol else 1e-4, args.lower_bound if args.lower_bound else 500, "strong"
         p.scale = n_side * n_side / 1e6
         p.workload = (f"config 4: {n_side * n_side}-point jittered torus cloud, symmetrised 8-NN graph Laplacian ({lhs.nnz} stored entries), "
                       f"M=I/N, Poisson lhs=1e-6*M+L, fp64, K=1, V-cycle {args.sweeps}+{args.sweeps} sweeps, lower_bound={p.lower_bound}, "
@@ -498,7 +502,8 @@ def main():
         per = len(tt_ns) // iters_tr
         dt = np.diff(tt_ns).astype(np.float64) * 1e-3
         names = {0: "restrict", 1: "jacobi", 2: "residual", 3: "prolong_add", 4: "norm", 5: "norm+jacobi", 6: "defect+norm"}
-        other = {100: "stopping_test", 101: "coarse_Wb", 102: "coarse_Wty", 103: "peer_push", 104: "peer_norm"}
+        other = {100: "stopping_test", 101: "coarse_Wb", 102: "coarse_Wty", 103: "peer_push", 104: "peer_norm", 105: "cluster_tail", 106: "cluster_tail_staged", 110: "ct_restrict", 111: "ct_jacobi", 112: "ct_residual",
+                 113: "ct_prolong_add", 120: "ct_dense_matvec"}
         for k in range(per):
             idx = np.arange(per + k, len(tt_ns) - 1, per)
             idx = idx[idx < len(dt)]

@@ -166,6 +166,7 @@ int gmg_set_option(gmg_handle h, const char* key, double value) {
         else if (k == "fp32_refine") s.fp32_refine = value != 0.0, cycle = true;
         else if (k == "l2_hints") s.l2_hints = value != 0.0, cycle = true;
         else if (k == "tail_rows") s.tail_rows = (int)value, cycle = true;
+        else if (k == "cluster_tail_rows") s.cluster_tail_rows = (int)value, cycle = true;
         else if (k == "dist_graph") s.dist_graph = value != 0.0, cycle = true;
         else if (k == "kernel_path") s.kernel_path = (int)value, hierarchy = true;
         else if (k == "xfer_threads") s.xfer_threads = (int)value;
@@ -230,6 +231,7 @@ int gmg_get_option(gmg_handle h, const char* key, double* value) {
         else if (k == "fp32_refine") *value = s.fp32_refine;
         else if (k == "l2_hints") *value = s.l2_hints;
         else if (k == "tail_rows") *value = s.tail_rows;
+        else if (k == "cluster_tail_rows") *value = s.cluster_tail_rows;
         else if (k == "dist_graph") *value = s.dist_graph;
         else if (k == "kernel_path") *value = s.kernel_path;
         else if (k == "xfer_threads") *value = s.xfer_threads;

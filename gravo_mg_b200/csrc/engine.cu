@@ -16,6 +16,7 @@
 #include "peer_exchange.h"
 #include "solver.h"
 #include "sparse_kernels.h"
+#include "cluster_tail.cuh"
 #include "tail_kernel.cuh"
 
 namespace gmg {
@@ -1719,9 +1720,17 @@ private:
         // levels small enough to live in L2 and be launch-latency bound run as one persistent
         // kernel (tail_kernel.cuh); never the finest level, whose streaming kernels are better
         tail_level_ = -1, tail_begin_ = tail_end_ = 0;
+        tail_cluster_ = false;
         for (int k = 1; k <= n_levels_ && st_->tail_rows > 0 && st_->dist.world <= 1 && p.cycle_type == 0; ++k)
             if (lv_[k].n <= st_->tail_rows) {
                 tail_level_ = k;
+                break;
+            }
+        // ... or, the default: the levels of a few thousand rows as one thread-block cluster (cluster_tail.cuh)
+        for (int k = 1; k < n_levels_ && tail_level_ < 0 && st_->cluster_tail_rows > 0 && st_->dist.world <= 1 && p.cycle_type == 0; ++k)
+            if (lv_[k].n <= st_->cluster_tail_rows) {
+                tail_level_ = k;
+                tail_cluster_ = true;
                 break;
             }
         if (n_levels_ == 0) {
@@ -1907,14 +1916,98 @@ private:
                 }
             }
         }
+        if (tail_cluster_ && !plan_cluster_tail(table)) {
+            tail_level_ = -1;  // does not fit one cluster's shared memory: the per-operator kernels stay
+            return;
+        }
         tail_table_.ensure(table.size() * sizeof(TailOp<T>));
         GMG_CUDA(cudaMemcpyAsync(tail_table_.ptr, table.data(), table.size() * sizeof(TailOp<T>), cudaMemcpyHostToDevice, stream_));
         GMG_CUDA(cudaStreamSynchronize(stream_));  // `table` is a local
         n_tail_ops_ = (int)table.size();
+        cluster_args_.ops = tail_table_.ptr, cluster_args_.n_ops = n_tail_ops_, cluster_args_.ctl = ctl_.ptr;
         Op tail;
         tail.kind = OP_TAIL, tail.level = tail_level_;
         ops_.erase(ops_.begin() + tail_begin_, ops_.begin() + tail_end_);
         ops_.insert(ops_.begin() + tail_begin_, tail);
+    }
+
+    // Cluster tail: number the sparse operators of the table, pick the cluster size and the shared memory one CTA
+    // needs for its slabs of all of them (worst CTA), choose the threads per row. False: does not fit.
+    bool plan_cluster_tail(std::vector<TailOp<T>>& table) {
+        cluster_args_ = ClusterTailArgs();
+        std::vector<const std::vector<int>*> host_rp;
+        for (TailOp<T>& op : table) {
+            if (op.kind != TAIL_ROWS) continue;
+            int m = -1;
+            for (int j = 0; j < cluster_args_.n_mats; ++j)
+                if (cluster_args_.mats[j].rowptr == op.a.rowptr && cluster_args_.mats[j].vals == (const void*)op.a.vals) m = j;
+            if (m < 0) {
+                if (cluster_args_.n_mats == kClusterTailMaxMats) return false;
+                const std::vector<int>* rp = nullptr;
+                for (int k = 0; k <= n_levels_ && !rp; ++k) {
+                    if (op.a.rowptr == lv_[k].A.indptr.ptr) rp = &st_->a_pat[k].indptr;
+                    if (k < n_levels_ && op.a.rowptr == lv_[k].P.indptr.ptr) rp = &st_->hier.U[k].indptr;
+                    if (k < n_levels_ && op.a.rowptr == lv_[k].R.indptr.ptr) rp = &st_->r_host[k].indptr;
+                }
+                if (!rp) return false;
+                m = cluster_args_.n_mats++;
+                cluster_args_.mats[m].rowptr = op.a.rowptr, cluster_args_.mats[m].colidx = op.a.colidx;
+                cluster_args_.mats[m].vals = op.a.vals, cluster_args_.mats[m].n_rows = op.a.n_rows;
+                host_rp.push_back(rp);
+            }
+            op.mat = m;
+        }
+        auto kernel = cluster_tail_kernel<T>;
+        static bool opted_in = false;
+        if (!opted_in) {
+            cudaFuncAttributes attr;
+            GMG_CUDA(cudaFuncGetAttributes(&attr, kernel));
+            GMG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(staged_smem_limit() - attr.sharedSizeBytes)));
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            cudaGetLastError();
+            opted_in = true;
+        }
+        cudaFuncAttributes attr;
+        GMG_CUDA(cudaFuncGetAttributes(&attr, kernel));
+        for (int C : {16, 8}) {
+            size_t worst = 0;
+            for (int r = 0; r < C; ++r) {
+                size_t bytes = 128;
+                for (int m = 0; m < cluster_args_.n_mats; ++m) {
+                    const std::vector<int>& rp = *host_rp[m];
+                    const int n = cluster_args_.mats[m].n_rows;
+                    const int r0 = (int)((long long)n * r / C), r1 = (int)((long long)n * (r + 1) / C);
+                    const size_t n_rp = (size_t)(((r1 + 1 + 3) & ~3) - (r0 & ~3));
+                    const size_t cnt = (size_t)(((rp[r1] + 3) & ~3) - (rp[r0] & ~3));
+                    bytes += n_rp * 4 + ((cnt * sizeof(T) + 15) & ~(size_t)15) + ((cnt * 4 + 15) & ~(size_t)15);
+                }
+                worst = std::max(worst, bytes);
+            }
+            if (worst + attr.sharedSizeBytes > staged_smem_limit()) continue;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)C, 1, 1), cfg.blockDim = dim3(kClusterTailThreads, 1, 1), cfg.dynamicSmemBytes = worst;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)C, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+            cfg.attrs = at, cfg.numAttrs = 1;
+            int n_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&n_clusters, kernel, &cfg) != cudaSuccess || n_clusters < 1) {
+                cudaGetLastError();
+                continue;
+            }
+            cluster_size_ = C, cluster_smem_ = worst;
+            // threads per row: as many as fill the cluster in one pass, at most 8 and at most the row length
+            for (TailOp<T>& op : table) {
+                if (op.kind != TAIL_ROWS) continue;
+                const int64_t threads = (int64_t)C * kClusterTailThreads;
+                const double avg = op.a.n_rows ? (double)((*host_rp[op.mat])[op.a.n_rows]) / op.a.n_rows : 1.0;
+                int lanes = 1;
+                while (lanes < 8 && lanes * 2 <= avg && (int64_t)op.a.n_rows * lanes * 2 <= threads) lanes *= 2;
+                op.lanes = lanes;
+            }
+            return true;
+        }
+        return false;
     }
 
     int run_op(const Op& op, cudaStream_t s, unsigned long long cond) {
@@ -1988,6 +2081,20 @@ private:
                 break;
             }
             case OP_TAIL: {
+                if (tail_cluster_) {
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3((unsigned)cluster_size_, 1, 1), cfg.blockDim = dim3(kClusterTailThreads, 1, 1);
+                    cfg.dynamicSmemBytes = cluster_smem_, cfg.stream = s;
+                    cudaLaunchAttribute at[2];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = (unsigned)cluster_size_, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+                    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    at[1].val.programmaticStreamSerializationAllowed = 1;
+                    cfg.attrs = at, cfg.numAttrs = st_->use_pdl ? 2 : 1;
+                    GMG_CUDA(cudaLaunchKernelEx(&cfg, cluster_tail_kernel<T>, cluster_args_));
+                    launches += 1;
+                    break;
+                }
                 const int sms = tail_grid();
                 tail_kernel<T><<<sms, kTailThreads, 0, s>>>(reinterpret_cast<const TailOp<T>*>(tail_table_.ptr), n_tail_ops_, tail_bar_.ptr);
                 GMG_CUDA(cudaGetLastError());
@@ -2201,6 +2308,10 @@ private:
     bool numeric_ready_ = false;
     std::vector<Op> ops_, prologue_;
     int tail_level_ = -1, n_tail_ops_ = 0, tail_grid_ = 0;
+    bool tail_cluster_ = false;        // the tail runs as one thread-block cluster (cluster_tail.cuh), not as a grid with L2 barriers
+    ClusterTailArgs cluster_args_;
+    int cluster_size_ = 0;
+    size_t cluster_smem_ = 0;
     size_t tail_begin_ = 0, tail_end_ = 0;
     DeviceBuffer<unsigned char> tail_table_;
     DeviceBuffer<unsigned> tail_bar_;

@@ -66,6 +66,9 @@ struct SolverState {
     std::vector<unsigned long long> trace_log;
     int tail_rows = 0;               // levels with at most this many rows run inside the fused tail kernel; off by
                                      // default: measured slower than PDL-chained kernels ("Coarse tail")
+    int cluster_tail_rows = 0;       // > 0: levels from the first one with at most this many rows down run as ONE thread-block cluster
+                                     // (cluster_tail.cuh): operators staged in shared memory, hardware cluster barriers. Off by
+                                     // default: measured 49 us against 32 us for the PDL-chained kernels it replaces (config 2)
     bool dist_graph = true;          // multi-GPU: capture the cycle (kernels + NCCL exchanges) into a CUDA graph
     bool p2p = true;                 // multi-GPU: halos and norms through NVLink peer memory (peer_exchange.h);
                                      // false: pack / ncclSend / ncclRecv / unpack and ncclAllReduce

@@ -23,6 +23,7 @@ struct TailOp {
     int epi = EPI_SPMV;     // TAIL_ROWS
     int lanes = 8;          // TAIL_ROWS: threads per row (1, 2, 4 or 8), chosen so one pass covers the level
     int kcols = 1;          // columns handled by this operator (1..4)
+    int mat = -1;           // TAIL_ROWS inside the cluster kernel (cluster_tail.cuh): index of the staged operator
     SpmvArgs<T> a;          // TAIL_ROWS
     // TAIL_COLDOT: out[c, k] = sum over the stored triangle of column c of M of M[r, c] * v[r, k]
     const double* M = nullptr;

@@ -22,10 +22,16 @@ def main():
 
     out = {}
     for name, (n_side, replicate_rows, kind) in {"two_sharded_levels": (300, 5000, "poisson"), "one_sharded_level": (300, 50000, "poisson"),
-                                                 "smoothing_K3": (200, 3000, "smoothing")}.items():
-        V, F = synth.torus_grid(n_side, n_side)
-        V, S, M, neigh = synth.mesh_operators(V, F)
-        lhs, rhs = synth.poisson_system(S, M) if kind == "poisson" else synth.smoothing_system(V, S, M)
+                                                 "smoothing_K3": (200, 3000, "smoothing"), "knn_cloud": (240, 4000, "cloud")}.items():
+        if kind == "cloud":  # BASELINE config 4 in small: jittered torus cloud, symmetrised 8-NN graph Laplacian, M = I / N
+            V = synth.torus_cloud(n_side, seed=0)
+            S, M = synth.knn_graph_laplacian(synth.knn_grid(V, n_side, k=8))
+            neigh = gravomg.util.neighbors_from_stiffness(S)
+            lhs, rhs = synth.poisson_system(S, M)
+        else:
+            V, F = synth.torus_grid(n_side, n_side)
+            V, S, M, neigh = synth.mesh_operators(V, F)
+            lhs, rhs = synth.poisson_system(S, M) if kind == "poisson" else synth.smoothing_system(V, S, M)
         kw = dict(lower_bound=500, tolerance=1e-6, device=local)
         single = gravomg.MultigridSolver(V, neigh, M, **kw)
         single.solver.set_option("lanes", 1)

@@ -424,6 +424,40 @@ def test_fused_coarse_tail_matches_per_operator_kernels(ico10k, torus_mid):
         assert abs(int(o.solver_timing["iterations"]) - int(iters)) <= 1
 
 
+@pytest.mark.parametrize("kind", ["poisson", "smoothing_K3", "float32"])
+def test_cluster_tail_matches_per_operator_kernels(torus_mid, kind):
+    """Option cluster_tail_rows: the levels from the first one with <= that many rows down run as ONE thread-block
+    cluster (operators staged in shared memory by bulk copies, hardware cluster barriers between operators,
+    cluster_tail.cuh). Same arithmetic as the per-operator kernels up to the lane split of the row sums."""
+    p = torus_mid
+    lhs, rhs = (p.lhs, p.rhs) if kind == "poisson" else ((p.M + 1e-3 * p.S).tocsr(), p.M @ p.V)
+    kw = dict(lower_bound=50, tolerance=1e-6 if kind != "float32" else 1e-4)
+    if kind == "float32":
+        kw["dtype"] = "float32"
+    xs, iters, launches = [], [], []
+    for rows in (0, 8192, 30000):
+        solver = p.new_solver(**kw)
+        solver.solver.set_option("cluster_tail_rows", rows)
+        solver.solver.set_option("trace", 1)
+        xs.append(solver.solve(lhs, rhs))
+        iters.append(int(solver.solver_timing["iterations"]))
+        _, tags = solver.solver.trace()
+        launches.append(int((tags == 105).sum()))
+        sizes = [lv["rows"] for lv in solver.solver.level_info()]
+    assert len(sizes) >= 5 and sizes[2] <= 8192 < sizes[1] <= 30000
+    # 0: off. 8192: levels 2.. in the cluster kernel, once per cycle. 30000: level 1 would join, but its operators
+    # do not fit the shared memory of one cluster -> the per-operator kernels stay (same bits as off)
+    assert launches[0] == 0 and launches[1] == iters[1] and launches[2] == 0
+    np.testing.assert_array_equal(xs[0], xs[2])
+    assert abs(iters[0] - iters[1]) <= 1
+    if kind == "float32":  # fp32 levels correct an fp64 iterate: both runs end below the tolerance, judged by the oracle
+        assert oracle.residual_check(lhs, rhs, xs[1], 2, p.m) <= 1e-4 * (1 + 1e-3)
+        assert p.mnorm(xs[0] - xs[1]) <= 2e-4 * p.mnorm(xs[0])
+    else:
+        bound = 50 * EPS * abs(lhs).sum(0).max() * np.linalg.norm(xs[0])
+        assert np.linalg.norm(lhs @ (xs[0] - xs[1])) <= bound
+
+
 def test_kernel_paths_agree(ico10k):
     p = ico10k
     xs = []

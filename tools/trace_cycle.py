@@ -15,7 +15,9 @@ import gravomg  # noqa: E402
 from gravo_mg_b200 import synth  # noqa: E402
 
 EPI = {0: "restrict/spmv", 1: "jacobi", 2: "residual", 3: "prolong_add", 4: "norm", 5: "norm+jacobi"}
-OTHER = {100: "stopping test", 101: "coarse W b", 102: "coarse W^T y", 103: "peer push kernel", 104: "peer norm"}
+OTHER = {100: "stopping test", 101: "coarse W b", 102: "coarse W^T y", 103: "peer push kernel", 104: "peer norm", 105: "coarse tail (cluster kernel): dependency met", 106: "  cluster tail: slabs staged",
+         110: "  cluster tail: restrict", 111: "  cluster tail: jacobi", 112: "  cluster tail: residual", 113: "  cluster tail: prolong_add",
+         120: "  cluster tail: dense mat-vec", 130: "  cluster tail: cast", 140: "  cluster tail: cast", 150: "  cluster tail: zero"}
 
 
 def main():
