@@ -467,28 +467,65 @@ def main():
     converged = unconverged == 0
     value = p.scale * cycles / (dev_ms_max / 1e3)  # all ranks run the same cycles of one sharded system
 
-    # ---- end to end through the public API, host arrays in, host array out
-    x = solver.solve(p.lhs, p.rhs)
-    barrier()
-    e2e_t0 = time.perf_counter()
-    e2e_cycles = 0
-    e2e_split = {"stage_host_ms": 0.0, "device_solve_ms": 0.0, "fetch_host_ms": 0.0}
-    for _ in range(args.steps):
-        x = solver.solve(p.lhs, p.rhs)
-        e2e_cycles += int(solver.solver_timing["iterations"])
-        tt = b.transfer_timing()
-        e2e_split["stage_host_ms"] += tt["stage_host_ms"] / args.steps
-        e2e_split["fetch_host_ms"] += tt["fetch_host_ms"] / args.steps
-        e2e_split["device_solve_ms"] += solver.solver_timing["solver_total"] / args.steps
-    e2e_split["transfer_threads"] = tt["transfer_threads"]
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - e2e_t0)
+    # ---- end to end through the public API, host arrays in, host array out. Headline: the caller keeps lhs.data, rhs and
+    # the result array in page-locked memory (views of torch pinned tensors), so the copy engine reads / writes them
+    # directly; the pageable variant (values staged through the library's pinned chunks by worker threads) beside it.
+    def run_e2e(lhs_h, rhs_h, out_h):
+        x = solver.solve(lhs_h, rhs_h, out=out_h)
+        barrier()
+        t0 = time.perf_counter()
+        cyc = 0
+        sp = {"stage_host_ms": 0.0, "device_solve_ms": 0.0, "fetch_host_ms": 0.0}
+        for _ in range(args.steps):
+            x = solver.solve(lhs_h, rhs_h, out=out_h)
+            cyc += int(solver.solver_timing["iterations"])
+            tt = b.transfer_timing()
+            sp["stage_host_ms"] += tt["stage_host_ms"] / args.steps
+            sp["fetch_host_ms"] += tt["fetch_host_ms"] / args.steps
+            sp["device_solve_ms"] += solver.solver_timing["solver_total"] / args.steps
+        sp["transfer_threads"] = tt["transfer_threads"]
+        barrier()
+        return x, cyc, max_over_ranks(time.perf_counter() - t0), sp, tt
+
+    def pinned_copy(a):
+        t = torch.empty(a.shape, dtype=torch.float64).pin_memory()
+        v = t.numpy()
+        v[...] = a
+        return v, t
+
+    x, pg_cycles, pg_s, pg_split, _ = run_e2e(p.lhs, p.rhs, None)
+    data_pin, keep1 = pinned_copy(p.lhs.data)
+    rhs_pin, keep2 = pinned_copy(p.rhs if p.rhs.ndim == 2 else p.rhs[:, None])
+    out_pin, keep3 = pinned_copy(np.zeros_like(rhs_pin))
+    lhs_pin = p.lhs.copy()
+    lhs_pin.data = data_pin
+    x, e2e_cycles, e2e_s, e2e_split, tt = run_e2e(lhs_pin, rhs_pin, out_pin)
     clocks = sampler.stop()
     e2e_value = p.scale * e2e_cycles / e2e_s
     lhs, rhs = p.lhs, p.rhs
     h2d = lhs.indptr.nbytes // (lhs.indptr.itemsize // 4) + lhs.indices.nbytes // (lhs.indices.itemsize // 4) + lhs.data.nbytes + rhs.nbytes
     h2d_step = int(tt["h2d_bytes"])  # what this rank copied per solve (the pattern is compared on the host and not re-sent)
     d2h = x.nbytes
+
+    # ---- the same solve with conjugate gradients around the cycle (option krylov = 1; secondary number: fewer
+    # iterations to the tolerance, each one cycle + one product with A)
+    krylov = None
+    if world == 1 and p.K <= 4 and p.dtype == "float64":
+        b.set_option("krylov", 1)
+        for _ in range(2):
+            b.solve_staged()
+        k_ms, k_it = 0.0, 0
+        for _ in range(min(args.steps, 5)):
+            b.solve_staged()
+            tk = b.solver_timing()
+            k_ms += tk["solver_total"]
+            k_it += int(tk["iterations"])
+        n_k = min(args.steps, 5)
+        krylov = {"what": "conjugate gradients preconditioned with one V-cycle (option krylov=1), device time per solve",
+                  "iterations_per_solve": k_it / n_k, "ms_per_solve": k_ms / n_k, "residue": tk["residue"],
+                  "converged": bool(tk["residue"] <= p.tol)}
+        b.set_option("krylov", 0)
+        b.solve_staged()
 
     # ---- in-cycle timing of every kernel: device globaltimer trace of one more solve (start-to-start cadence)
     b.set_option("trace", 1)
@@ -598,8 +635,11 @@ def main():
             "dtype": "f32" if p.dtype == "float32" else "f64", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value if converged else None, "unit": unit, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s / args.steps, "split": e2e_split,
-                    "note": (f"caller-owned pageable numpy arrays; this rank's values + rhs go through pinned chunks filled by host threads; the CSR "
-                             f"pattern ({h2d - lhs.data.nbytes - rhs.nbytes} B) is compared against the staged one on the host and not re-sent")},
+                    "note": (f"caller-owned page-locked numpy arrays (lhs.data, rhs, result: views of torch pinned tensors) copied directly by the "
+                             f"copy engine; this rank's share of values + rhs per solve; the CSR pattern ({h2d - lhs.data.nbytes - rhs.nbytes} B) is "
+                             f"compared against the staged one on the host and not re-sent"),
+                    "pageable": {"value": p.scale * pg_cycles / pg_s if converged else None, "ms_per_step": 1e3 * pg_s / args.steps, "split": pg_split,
+                                 "note": "the same call with ordinary pageable numpy arrays: values staged through pinned chunks by worker threads"}},
             "gpu_launches": int(launches), "roofline": roofline,
             "smoother": (f"Chebyshev-weighted Jacobi, band rho/{args.cheb_alpha:g}..rho" if args.smoother == "chebyshev"
                          else f"damped Jacobi omega={args.omega:.4f}") + f", {args.sweeps}+{args.sweeps} sweeps",
@@ -610,6 +650,8 @@ def main():
             "wall_s_timed_region": wall, "last_step_split_ms": split, "per_kernel_us": per_kernel,
             "host_setup_s": {"hierarchy": hierarchy_s, "first_stage_incl_symbolic_setup": first_stage_s},
         }
+        if krylov:
+            line["krylov"] = krylov
         if not converged:
             line["unconverged_value"] = value
             line["note"] = f"{unconverged} of {args.steps} solves stopped at max_iter above the tolerance: no value reported"

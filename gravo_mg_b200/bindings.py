@@ -125,10 +125,18 @@ class MultigridSolver:
         return x
 
     # ------------------------------------------------------------------ the hot path
-    def solve(self, lhs, rhs):
+    def solve(self, lhs, rhs, out=None):
+        """core.cpp:68-72. ``out`` (addition): a C-contiguous float64 array of the result's shape to write into —
+        with page-locked arrays for ``lhs.data``, ``rhs`` and ``out`` (e.g. views of ``torch.Tensor.pin_memory()``) the
+        copy engine reads and writes the caller's buffers directly instead of staging them through pinned chunks."""
         ap, ai, ad = _csr_arrays(lhs, self._n)
         b = _dense_rhs(rhs, self._n)
-        x = np.empty_like(b)
+        if out is None:
+            x = np.empty_like(b)
+        else:
+            x = out
+            if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous and x.shape == b.shape):
+                raise ValueError(f"out must be a C-contiguous float64 array of shape {b.shape}")
         check(self._h, lib.gmg_solve(self._h, self._n, i32(ap), i32(ai), f64(ad), f64(b), f64(x), b.shape[1]))
         return x
 

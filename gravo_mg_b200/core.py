@@ -35,8 +35,10 @@ class MultigridSolver(object):
         """Creates the Gravo MG solver for linear systems on curved surfaces (meshes and point clouds).
 
         Arguments have the meaning documented upstream (core.py:14-47): ``pos`` (N, 3) positions,
-        ``neigh`` (N, max_neighbors) int32 neighbour array padded with -1, ``mass`` the (lumped)
-        mass matrix; the hierarchy is built in the constructor.
+        ``neigh`` (N, max_neighbors) int32 neighbour array padded with -1, ``mass`` the LUMPED (diagonal)
+        mass matrix — a matrix with off-diagonal entries is rejected (upstream's residualCheck would accept a
+        consistent mass matrix; every caller of the reference passes a lumped one); the hierarchy is built
+        in the constructor.
         """
         super().__init__()
         if not mass.getformat() == "csr":
@@ -63,12 +65,13 @@ class MultigridSolver(object):
         assert hierarchy_type == Hierarchy.OURS or (hierarchy_type == Hierarchy.SIG21 and self.sig21_computed)
         self.solver.toggle_hierarchy(hierarchy_type)
 
-    def solve(self, lhs, rhs):
-        """Solves a linear system Ax = b, where lhs is A (scipy sparse) and rhs is b ((N,) or (N, K))."""
+    def solve(self, lhs, rhs, out=None):
+        """Solves a linear system Ax = b, where lhs is A (scipy sparse) and rhs is b ((N,) or (N, K)).
+        ``out`` (addition, optional): array to write the solution into (see bindings.MultigridSolver.solve)."""
         if not lhs.getformat() == "csr":
             print("LHS is not in CSR format, converting to CSR")
             lhs = lhs.tocsr()
-        return self.solver.solve(lhs, rhs)
+        return self.solver.solve(lhs, rhs, out)
 
     def direct_solve(self, lhs, rhs, pardiso=False):
         return self.solver.direct_solve(lhs, rhs, pardiso)

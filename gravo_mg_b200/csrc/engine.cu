@@ -1418,7 +1418,8 @@ private:
     // option xfer_threads is 0 (plain cudaMemcpyAsync from pageable memory).
     HostTransfer* transfer() {
         int want = st_->xfer_threads;
-        if (want < 0) want = std::min(8, std::max(1, (int)std::thread::hardware_concurrency() / 2));
+        // auto: the host cores of this rank's share of the box (one process per GPU), at most 16
+        if (want < 0) want = std::min(16, std::max(2, (int)std::thread::hardware_concurrency() / std::max(1, st_->dist.world)));
         if (want == 0) {
             xfer_.reset();
             return nullptr;

@@ -27,6 +27,7 @@ namespace gmg {
 class HostTransfer {
 public:
     static constexpr size_t kChunk = 2u << 20;
+    static constexpr size_t kDownChunk = 256u << 10;  // downloads: small chunks so that every worker copies out a share
     static constexpr int kSlots = 2;
 
     HostTransfer(int device, int threads) : device_(device) {
@@ -81,8 +82,16 @@ public:
         std::vector<Task> tasks;
         // comparisons are spread between the copy chunks so that both progress from the start
         std::vector<Task> cp, cm;
-        for (size_t i = 0; i < copies.size(); ++i)
+        for (size_t i = 0; i < copies.size(); ++i) {
+            if (copies[i].bytes && page_locked(copies[i].host)) {
+                // the caller's buffer is page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory): the copy
+                // engine reads it directly, no staging through the workers' pinned slots
+                cudaStream_t cs = copies[i].stream ? copies[i].stream : stream;
+                GMG_CUDA(cudaMemcpyAsync(copies[i].dev, copies[i].host, copies[i].bytes, cudaMemcpyHostToDevice, cs));
+                continue;
+            }
             for (size_t o = 0; o < copies[i].bytes; o += kChunk) cp.push_back({0, i, o, std::min(kChunk, copies[i].bytes - o)});
+        }
         for (size_t i = 0; i < compares.size(); ++i)
             for (size_t o = 0; o < compares[i].bytes; o += kChunk) cm.push_back({1, i, o, std::min(kChunk, compares[i].bytes - o)});
         size_t a = 0, b = 0;
@@ -116,10 +125,15 @@ public:
 
     // Synchronous device -> caller buffer copy. The producer of `dev` must have completed.
     void download(void* host, const void* dev, size_t bytes) {
-        const size_t n = (bytes + kChunk - 1) / kChunk;
+        if (bytes && page_locked(host)) {  // page-locked destination: one direct copy
+            GMG_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, workers_[0].stream));
+            GMG_CUDA(cudaStreamSynchronize(workers_[0].stream));
+            return;
+        }
+        const size_t n = (bytes + kDownChunk - 1) / kDownChunk;
         parallel_for(n, [&](size_t i, int t) {
             Worker& w = workers_[t];
-            const size_t off = i * kChunk, len = std::min(kChunk, bytes - off);
+            const size_t off = i * kDownChunk, len = std::min(kDownChunk, bytes - off);
             const int slot = w.next_slot;
             w.next_slot = (slot + 1) % kSlots;
             if (w.used[slot]) GMG_CUDA(cudaEventSynchronize(w.ev[slot]));
@@ -129,6 +143,16 @@ public:
             GMG_CUDA(cudaStreamSynchronize(w.stream));
             std::memcpy((char*)host + off, pin, len);
         });
+    }
+
+    // Is this host address inside page-locked memory known to CUDA?
+    static bool page_locked(const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return a.type == cudaMemoryTypeHost;
     }
 
 private:

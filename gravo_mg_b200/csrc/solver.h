@@ -97,7 +97,7 @@ struct SolverState {
     bool spgemm_plan = true;         // Galerkin products from index-pair lists built once per pattern
     long long spgemm_plan_max_pairs = 1500000000ll;  // 12 GB of pairs; beyond it levels fall back to the searching kernel
     int xfer_threads = -1;           // host threads staging caller buffers through pinned chunks (host_xfer.h);
-                                     // -1 = min(8, cores / 2), 0 = plain pageable cudaMemcpyAsync
+                                     // -1 = cores / ranks (2..16), 0 = plain pageable cudaMemcpyAsync
     // ---- symbolic phase (host): patterns of every level operator for the staged lhs pattern
     std::vector<HostCsr> r_host;     // R[k] = U[k]^T
     std::vector<HostCsr> a_pat;      // pattern of A_k, k = 0..L (values unused)

@@ -77,3 +77,31 @@ def test_direct_solve_large_system_runs_cg_to_the_rounding_floor(torus_mid):
     assert p.mnorm(x - xd) <= 1e-11 * p.mnorm(xd)
     assert s.solver_timing["direct_residual"] <= 1e-12
     assert s.solver.get_option("krylov") == 0 and s.solver.get_option("tolerance") == 1e-4  # settings restored
+
+
+def test_solve_with_page_locked_caller_buffers(ico10k):
+    """lhs.data, rhs and ``out`` in page-locked memory (views of torch pinned tensors): the copy engine reads and
+    writes them directly (host_xfer.h); same bits as the staged pageable path."""
+    import torch
+
+    p = ico10k
+    s = p.new_solver(tolerance=1e-6)
+    x_ref = s.solve(p.lhs, p.rhs)
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float64).pin_memory()
+        v = t.numpy()
+        v[...] = a
+        return v, t
+
+    data, k1 = pinned(p.lhs.data)
+    rhs, k2 = pinned(p.rhs)
+    out, k3 = pinned(np.zeros_like(p.rhs))
+    lhs = p.lhs.copy()
+    lhs.data = data
+    x = s.solve(lhs, rhs, out=out)
+    assert x is out
+    np.testing.assert_array_equal(x, x_ref)
+    assert s.solver.transfer_timing()["pattern_reused"] == 1.0
+    with pytest.raises(ValueError):
+        s.solve(lhs, rhs, out=np.zeros((3, 1)))

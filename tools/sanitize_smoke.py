@@ -1,0 +1,69 @@
+"""A small solve that touches every kernel family, for compute-sanitizer (memcheck / racecheck / synccheck):
+
+  compute-sanitizer --tool memcheck  python tools/sanitize_smoke.py
+  compute-sanitizer --tool racecheck python tools/sanitize_smoke.py
+  compute-sanitizer --tool memcheck --target-processes all python -m torch.distributed.run --nproc-per-node 2 \\
+        --master-addr 127.0.0.1 tools/sanitize_smoke.py            (sharded: peer-memory exchange)
+
+2 562-vertex icosphere, three levels: staged (TMA + mbarrier ring) and direct row-product kernels, Galerkin
+products with plans, the dataflow coarse factor (tile flags), while-graph, K = 1 and 3, fp32 levels, conjugate
+gradients, device assembly, the cluster tail."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+import torch  # noqa: E402
+
+import gravomg  # noqa: E402
+from gravo_mg_b200 import synth  # noqa: E402
+
+
+def main():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    V, F = synth.icosphere(4)
+    V, S, M, neigh = synth.mesh_operators(V, F)
+    lhs, rhs = synth.poisson_system(S, M)
+    lhs3, rhs3 = synth.smoothing_system(V, S, M)
+    done = []
+    s = gravomg.MultigridSolver(V, neigh, M, lower_bound=40, tolerance=1e-6, device=local)
+    if world > 1:
+        s.distribute(replicate_rows=300)
+    s.solve(lhs, rhs)
+    done.append(("poisson K=1", int(s.solver_timing["iterations"]), s.solver_timing["residue"]))
+    s.solve(lhs3, rhs3)
+    done.append(("smoothing K=3", int(s.solver_timing["iterations"]), s.solver_timing["residue"]))
+    if world == 1:
+        for opts in ({"kernel_path": 1}, {"cluster_tail_rows": 8192}, {"krylov": 1}, {"loop_mode": 0}):
+            t = gravomg.MultigridSolver(V, neigh, M, lower_bound=40, tolerance=1e-6, device=local)
+            for k, v in opts.items():
+                t.solver.set_option(k, v)
+            t.solve(lhs, rhs)
+            done.append((str(opts), int(t.solver_timing["iterations"]), t.solver_timing["residue"]))
+        f32 = gravomg.MultigridSolver(V, neigh, M, lower_bound=40, tolerance=1e-4, dtype="float32", device=local)
+        f32.solve(lhs3, rhs3)
+        done.append(("float32 levels", int(f32.solver_timing["iterations"]), f32.solver_timing["residue"]))
+        s.attach_mesh(F, V)
+        s.solver.mesh_stiffness()
+        s.conformal_flow(2, tau=0.01)
+        done.append(("device assembly + 2 flow steps", int(s.solver.transfer_timing()["flow_iterations"]), 0.0))
+        x = s.direct_solve(lhs3, rhs3)
+        done.append(("direct_solve", 1, float(np.abs(lhs3 @ x - rhs3).max())))
+    if local == 0:
+        for d in done:
+            print("sanitize_smoke:", d)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
