@@ -6,6 +6,7 @@
 // while-node so the whole loop is one launch.
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 #include "dense_coarse.h"
@@ -1970,7 +1971,9 @@ private:
         }
         cudaFuncAttributes attr;
         GMG_CUDA(cudaFuncGetAttributes(&attr, kernel));
+        const char* forced = std::getenv("GMG_CLUSTER_SIZE");  // measurement / debugging aid: 8 = portable cluster size only
         for (int C : {16, 8}) {
+            if (forced && std::atoi(forced) != C) continue;
             size_t worst = 0;
             for (int r = 0; r < C; ++r) {
                 size_t bytes = 128;
