@@ -385,6 +385,7 @@ int gmg_direct_solve(gmg_handle h, int64_t n, const int32_t* a_indptr, const int
                 d.n = n;
                 d.mass_diag = s.mass_diag;
                 d.hier.dof.push_back(n);
+                d.loop_mode = 0;  // one "cycle" (the dense solve) per call: no device-side loop needed
             }
             SolverState& d = s.direct_helper->s;
             d.params.stopping_criteria = s.params.stopping_criteria;

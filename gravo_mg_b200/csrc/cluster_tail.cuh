@@ -51,8 +51,11 @@ __device__ __forceinline__ unsigned cluster_n_ctas() {
     asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
     return r;
 }
+// All threads of all CTAs of the cluster. The warps arrive from divergent code (row loops with different trip counts,
+// single-thread trace marks), so the barrier must not be the .aligned form (synccheck: "divergent thread(s) in warp").
 __device__ __forceinline__ void cluster_barrier() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    __syncwarp();
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
 }
 
 // Where one CTA keeps its slab of one operator in shared memory.
@@ -215,7 +218,9 @@ __global__ void __launch_bounds__(kClusterTailThreads, 1) cluster_tail_kernel(co
     const unsigned rank = cluster_cta_rank(), n_ctas = cluster_n_ctas();
     const TailOp<T>* ops = static_cast<const TailOp<T>*>(args.ops);
 
-    // ---- stage this CTA's slab of every sparse operator (constant data: before the dependency wait)
+    // ---- stage this CTA's slab of every sparse operator (constant data: before the dependency wait); one lane of
+    // warp 0 issues, the warp stays together
+    if (threadIdx.x < 32) {
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         mbar_init_fence();
@@ -256,6 +261,8 @@ __global__ void __launch_bounds__(kClusterTailThreads, 1) cluster_tail_kernel(co
                 bulk_copy_g2s(const_cast<int*>(s.cols), cm.colidx + s.e0, cnt * (uint32_t)sizeof(int), bar);
             }
         }
+    }
+    __syncwarp();
     }
     __syncthreads();           // slabs[] visible
     grid_dependency_wait();    // vectors of the previous kernel of the cycle
