@@ -388,6 +388,16 @@ class MultigridSolver:
         check(self._h, lib.gmg_dist_ranges(self._h, int(level), out.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(rep)))
         return out, bool(rep.value)
 
+    def dist_windows(self, which):
+        """Row segments of the finest level this rank stores / uploads: ``which`` in 'A', 'U', 'Ut', 'rhs'.
+        Returns (list of (begin, end), enabled)."""
+        which = {"A": 0, "U": 1, "Ut": 2, "rhs": 3}[which] if isinstance(which, str) else int(which)
+        count, enabled = C.c_int64(0), C.c_int32(0)
+        check(self._h, lib.gmg_dist_windows(self._h, which, None, C.byref(count), C.byref(enabled)))
+        buf = np.zeros(2 * max(count.value, 1), dtype=np.int64)
+        check(self._h, lib.gmg_dist_windows(self._h, which, buf.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(count), C.byref(enabled)))
+        return [(int(buf[2 * i]), int(buf[2 * i + 1])) for i in range(count.value)], bool(enabled.value)
+
     def dist_halo(self, op, level, peer):
         """(send, recv) global index lists of operator ``op`` ('A', 'R', 'P') towards ``peer``."""
         op = {"A": 0, "R": 1, "P": 2}[op] if isinstance(op, str) else int(op)

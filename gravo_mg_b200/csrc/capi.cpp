@@ -551,6 +551,22 @@ int gmg_dist_layout(gmg_handle h, int64_t n, const int32_t* a_indptr, const int3
         require(n == h->s.n, "lhs has a different number of rows than the point set of the constructor");
         gmg::compute_level_patterns(h->s, n, a_indptr, a_indices);
         gmg::compute_dist_layout(h->s);
+        gmg::compute_level0_windows(h->s);
+    });
+}
+
+int gmg_dist_windows(gmg_handle h, int32_t which, int64_t* ranges, int64_t* count, int32_t* enabled) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(which >= 0 && which <= 3 && count && enabled, "bad argument");
+        const gmg::Level0Windows& w = h->s.win0;
+        const gmg::RowRanges& r = which == 0 ? w.a_rows : which == 1 ? w.p_rows : which == 2 ? w.c_rows : w.rhs_rows;
+        *enabled = w.on ? 1 : 0;
+        if (ranges) {
+            require(*count >= (int64_t)r.size(), "output buffer too small");
+            for (size_t i = 0; i < r.size(); ++i) ranges[2 * i] = r[i].first, ranges[2 * i + 1] = r[i].second;
+        }
+        *count = (int64_t)r.size();
     });
 }
 

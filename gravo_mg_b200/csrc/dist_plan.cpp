@@ -32,6 +32,25 @@ void build_ranges(const std::vector<int64_t>& level_rows, const std::vector<std:
     if (world <= 1) out.first_replicated = 0;
 }
 
+RowRanges merge_marked_rows(const std::vector<char>& mark, int64_t max_gap) {
+    RowRanges out;
+    const int64_t n_rows = (int64_t)mark.size();
+    for (int64_t r = 0; r < n_rows;) {
+        if (!mark[r]) {
+            ++r;
+            continue;
+        }
+        int64_t e = r + 1;
+        while (e < n_rows && mark[e]) ++e;
+        if (!out.empty() && r - out.back().second <= max_gap)
+            out.back().second = e;
+        else
+            out.emplace_back(r, e);
+        r = e;
+    }
+    return out;
+}
+
 HaloLists build_halo(const HostCsr& m, const std::vector<int64_t>& row_ranges, const std::vector<int64_t>& col_ranges,
                      int rank) {
     const int world = (int)row_ranges.size() - 1;

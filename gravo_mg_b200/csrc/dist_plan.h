@@ -40,6 +40,18 @@ struct DistLayout {
     int64_t end(int level) const { return ranges[level][rank + 1]; }
 };
 
+// Row segments of the finest level a rank stores and uploads (engine.cu, DevMat::segs): ascending, disjoint ranges.
+typedef std::vector<std::pair<int64_t, int64_t>> RowRanges;
+struct Level0Windows {
+    bool on = false;      // decided from the layout and the options only: identical on every rank
+    RowRanges a_rows;     // A_0 and A_0 U_0: own rows + the rows this rank's restriction gathers
+    RowRanges p_rows;     // U_0: own rows + every column of the rows above
+    RowRanges c_rows;     // U_0^T: this rank's coarse rows
+    RowRanges rhs_rows;   // right-hand side / x0: own rows + the entries of x this rank's rows gather (all rows when off)
+};
+// Marked rows as ascending ranges; gaps of at most max_gap unmarked rows are swallowed (fewer, larger segments).
+RowRanges merge_marked_rows(const std::vector<char>& mark, int64_t max_gap);
+
 // samples[k][c] = fine index (level k) of coarse point c (level k + 1); level_rows[k] = n_k.
 void build_ranges(const std::vector<int64_t>& level_rows, const std::vector<std::vector<int>>& samples, int world,
                   int64_t replicate_rows, DistLayout& out);

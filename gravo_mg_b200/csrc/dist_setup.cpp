@@ -48,4 +48,29 @@ void compute_dist_layout(SolverState& s) {
     }
 }
 
+void compute_level0_windows(SolverState& s) {
+    const DistLayout& d = s.dist;
+    Level0Windows& w = s.win0;
+    w = Level0Windows();
+    w.rhs_rows.assign(1, std::make_pair((int64_t)0, (int64_t)s.n));
+    const bool shard_setup = d.world > 1 && s.dist_shard_setup != 0;
+    w.on = shard_setup && s.dist_window && !s.hier.U.empty() && d.sharded(0);
+    if (!w.on) return;
+    const HostCsr& a0 = s.a_pat[0];
+    const HostCsr& r0 = s.r_host[0];
+    std::vector<char> ma((size_t)s.n, 0), mp((size_t)s.n, 0), mr((size_t)s.n, 0);
+    for (int64_t r = d.begin(0); r < d.end(0); ++r) ma[r] = mp[r] = mr[r] = 1;
+    for (int64_t I = d.begin(1); I < d.end(1); ++I)
+        for (int q = r0.indptr[I]; q < r0.indptr[I + 1]; ++q) ma[r0.indices[q]] = 1;
+    w.a_rows = merge_marked_rows(ma, 256);
+    for (const auto& rr : w.a_rows)
+        for (int q = a0.indptr[rr.first]; q < a0.indptr[rr.second]; ++q) mp[a0.indices[q]] = 1;
+    w.p_rows = merge_marked_rows(mp, 256);
+    w.c_rows.assign(1, std::make_pair(d.begin(1), d.end(1)));
+    // x0 = rhs: this rank reads its own rows of b and x plus the entries of x its rows gather
+    for (const auto& list : d.halo[HALO_A][0].recv)
+        for (int c : list) mr[c] = 1;
+    w.rhs_rows = merge_marked_rows(mr, 256);
+}
+
 }  // namespace gmg

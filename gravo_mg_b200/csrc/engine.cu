@@ -75,7 +75,7 @@ struct DevMat {
 
     const T* vals() const;
     // rows: ascending, disjoint, non-adjacent row ranges to store (nullptr: every row)
-    void upload_pattern(const HostCsr& m, cudaStream_t s, const std::vector<std::pair<int64_t, int64_t>>* rows_kept = nullptr) {
+    void upload_pattern(const HostCsr& m, cudaStream_t s, const RowRanges* rows_kept = nullptr) {
         rows = (int)m.rows, cols = (int)m.cols, nnz = m.nnz();
         segs.clear(), indptr_local.clear();
         if (rows_kept && !(rows_kept->size() == 1 && (*rows_kept)[0].first == 0 && (*rows_kept)[0].second == m.rows)) {
@@ -1189,46 +1189,11 @@ private:
         // products read (own range + the rows its restriction gathers), U_0 the rows those products and the
         // prolongation read, U_0^T this rank's coarse rows. HBM footprint and the per-solve upload of a rank are
         // ~1/world of the system (option dist_window = 0: whole operators everywhere).
-        const bool window0 = shard_setup && st_->dist_window && n_levels_ > 0 && d.sharded(0);
+        compute_level0_windows(*st_);
+        const bool window0 = st_->win0.on;
         window0_ = window0;
-        typedef std::vector<std::pair<int64_t, int64_t>> RowRanges;
-        auto ranges_of = [](const std::vector<char>& mark) {  // marked rows as ranges; gaps of <= 256 rows are kept too
-            RowRanges out;
-            const int64_t n_rows = (int64_t)mark.size();
-            for (int64_t r = 0; r < n_rows;) {
-                if (!mark[r]) {
-                    ++r;
-                    continue;
-                }
-                int64_t e = r + 1;
-                while (e < n_rows && mark[e]) ++e;
-                if (!out.empty() && r - out.back().second <= 256)
-                    out.back().second = e;
-                else
-                    out.emplace_back(r, e);
-                r = e;
-            }
-            return out;
-        };
-        RowRanges a_rows, p_rows, c_rows;
-        rhs_rows_.assign(1, std::make_pair((int64_t)0, (int64_t)st_->n));
-        if (window0) {
-            const HostCsr& a0 = st_->a_pat[0];
-            const HostCsr& r0 = st_->r_host[0];
-            std::vector<char> ma((size_t)st_->n, 0), mp((size_t)st_->n, 0), mr((size_t)st_->n, 0);
-            for (int64_t r = d.begin(0); r < d.end(0); ++r) ma[r] = mp[r] = mr[r] = 1;
-            for (int64_t I = d.begin(1); I < d.end(1); ++I)
-                for (int q = r0.indptr[I]; q < r0.indptr[I + 1]; ++q) ma[r0.indices[q]] = 1;
-            a_rows = ranges_of(ma);
-            for (const auto& rr : a_rows)
-                for (int q = a0.indptr[rr.first]; q < a0.indptr[rr.second]; ++q) mp[a0.indices[q]] = 1;
-            p_rows = ranges_of(mp);
-            c_rows.assign(1, std::make_pair(d.begin(1), d.end(1)));
-            // x0 = rhs: this rank reads its own rows of b and x plus the entries of x its rows gather
-            for (const auto& list : d.halo[HALO_A][0].recv)
-                for (int c : list) mr[c] = 1;
-            rhs_rows_ = ranges_of(mr);
-        }
+        const RowRanges &a_rows = st_->win0.a_rows, &p_rows = st_->win0.p_rows, &c_rows = st_->win0.c_rows;
+        rhs_rows_ = st_->win0.rhs_rows;
         int b = 0, e = -1;
         for (int k = 0; k < n_levels_; ++k) {
             const HostCsr& u = U[k];

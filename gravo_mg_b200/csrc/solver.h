@@ -104,6 +104,7 @@ struct SolverState {
     std::vector<HostCsr> ap_pat;     // pattern of A_k U_k, k = 0..L-1
     // ---- multi-GPU layout (world == 1: single GPU)
     DistLayout dist;
+    Level0Windows win0;              // multi-GPU: row segments of the finest level this rank stores (compute_level0_windows)
     int64_t replicate_rows = 300000; // levels with at most this many rows are replicated on every rank
     std::map<std::string, double> solver_timing;           // reference solverTiming keys
     std::map<std::string, double> transfer_timing;         // host side of the last stage / fetch (not a reference map)
@@ -121,6 +122,9 @@ std::unique_ptr<EngineBase> make_engine(SolverState* state);
 void compute_level_patterns(SolverState& s, int64_t n, const int* indptr, const int* indices);
 // Row ranges of every level and the halo lists of every sharded operator for s.dist.rank / world.
 void compute_dist_layout(SolverState& s);
+// Multi-GPU data decomposition of the finest level (after compute_dist_layout): which rows of A_0, A_0 U_0, U_0, U_0^T
+// and of the right-hand side this rank stores and uploads. Host only.
+void compute_level0_windows(SolverState& s);
 
 }  // namespace gmg
 

@@ -196,6 +196,11 @@ int gmg_dist_init(gmg_handle h, const void* id, int64_t size);
 /* Host-only: row ranges and halo lists for the given lhs pattern (what staging computes), so the
  * layout can be inspected and tested without a device. */
 int gmg_dist_layout(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t* a_indices);
+/* Data decomposition of the finest level (after gmg_dist_layout or staging): the row segments this rank stores and
+ * uploads per solve. which 0: rows of A_0 and A_0 U_0, 1: rows of U_0, 2: rows of U_0^T, 3: rows of the right-hand side.
+ * ranges receives (begin, end) pairs; query the number of pairs with ranges == NULL. *enabled = 0: whole operators are
+ * stored (single GPU, replicated finest level, options dist_window / dist_shard_setup off). Host only. */
+int gmg_dist_windows(gmg_handle h, int32_t which, int64_t* ranges, int64_t* count, int32_t* enabled);
 /* ranges[world + 1] of a level; *replicated = 1 when every rank computes all rows of it. */
 int gmg_dist_ranges(gmg_handle h, int32_t level, int64_t* ranges, int32_t* replicated);
 /* Halo lists of operator op (0: A_k, 1: R_k = U_k^T, 2: U_k) on a level towards one peer: global

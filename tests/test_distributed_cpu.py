@@ -126,3 +126,66 @@ def test_ranges_follow_the_samples():
     b.dist_configure(0, 1)
     b.dist_layout(lhs)
     assert b.dist_ranges(0)[1] is True
+
+
+def _rows(ranges):
+    return np.concatenate([np.arange(b, e) for b, e in ranges]) if ranges else np.zeros(0, dtype=np.int64)
+
+
+@pytest.mark.parametrize("mesh,world", [("torus", 2), ("torus", 4), ("torus", 8), ("ico", 3)])
+def test_finest_level_row_segments_hold_what_a_rank_reads(mesh, world):
+    """Data decomposition of the finest level (gmg_dist_windows, host only): for every rank the stored row segments
+    contain exactly what its kernels and its share of the Galerkin product read, they are ascending and disjoint,
+    and on a banded ordering a rank stores ~1/world of the operator — also on the periodic torus, where a rank's
+    halo wraps around to the other end of the index space (two or three segments, not one covering everything)."""
+    import gravomg
+    from gravo_mg_b200 import synth
+
+    V, F = synth.torus_grid(160, 160) if mesh == "torus" else synth.icosphere(5)
+    V, S, M, neigh = synth.mesh_operators(V, F)
+    lhs, _ = synth.poisson_system(S, M)
+    lhs = lhs.tocsr()
+    solver = gravomg.MultigridSolver(V, neigh, M, lower_bound=100)
+    U0 = solver.prolongation_matrices[0].tocsr()
+    R0 = U0.T.tocsr()
+    n = lhs.shape[0]
+    b = solver.solver
+    owned = np.zeros(n, dtype=int)
+    stored_fraction = []
+    for rank in range(world):
+        b.dist_configure(rank, world, 2000)
+        b.dist_layout(lhs)
+        fine, rep0 = b.dist_ranges(0)
+        coarse, _ = b.dist_ranges(1)
+        assert not rep0
+        (a_rows, on), (p_rows, _), (c_rows, _), (rhs_rows, _) = (b.dist_windows(w) for w in ("A", "U", "Ut", "rhs"))
+        assert on
+        for ranges in (a_rows, p_rows, c_rows, rhs_rows):  # ascending, disjoint
+            flat = np.array(ranges).ravel()
+            assert (np.diff(flat) >= 0).all()
+        assert all(e > s for s, e in a_rows + p_rows + rhs_rows)  # (a rank may own no coarse point: icosphere numbering)
+        own = np.arange(fine[rank], fine[rank + 1])
+        owned[own] += 1
+        A_set, P_set, rhs_set = set(_rows(a_rows).tolist()), set(_rows(p_rows).tolist()), set(_rows(rhs_rows).tolist())
+        assert set(own.tolist()) <= A_set and set(own.tolist()) <= P_set and set(own.tolist()) <= rhs_set
+        assert c_rows == [(int(coarse[rank]), int(coarse[rank + 1]))]
+        # rows of A_0 U_0 this rank's coarse rows are built from
+        gathered = np.unique(R0[coarse[rank]:coarse[rank + 1]].indices)
+        assert set(gathered.tolist()) <= A_set
+        # rows of U_0 the products of those rows read, and the entries of x0 = rhs the own rows gather
+        assert set(np.unique(lhs[_rows(a_rows)].indices).tolist()) <= P_set
+        assert set(np.unique(lhs[own].indices).tolist()) <= rhs_set
+        stored_fraction.append(lhs[_rows(a_rows)].nnz / lhs.nnz)
+        if mesh == "torus" and rank in (0, world - 1):
+            assert len(a_rows) >= 2  # own range + wrap-around halo at the other end of the index space
+    assert (owned == 1).all()  # the own ranges partition the rows
+    if mesh == "torus":
+        assert max(stored_fraction) <= 1.0 / world + 0.12, stored_fraction
+    # a single GPU, or the option off: whole operators
+    b.dist_configure(0, 1)
+    b.dist_layout(lhs)
+    assert b.dist_windows("A") == ([], False) and b.dist_windows("rhs") == ([(0, n)], False)
+    b.dist_configure(0, 2, 2000)
+    b.set_option("dist_window", 0)
+    b.dist_layout(lhs)
+    assert b.dist_windows("A")[1] is False
