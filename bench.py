@@ -232,6 +232,20 @@ def cpu_reference_run(p, U, steps, warmup, budget_s=150.0, repeats=1):
     (the reference pins itself to one OpenMP thread, multigrid_solver.cpp:86-87)."""
     from oracle import oracle
 
+    # one core, no migration (BASELINE.md §2: the reference is single-threaded by construction)
+    try:
+        allowed = os.sched_getaffinity(0)
+        os.sched_setaffinity(0, {sorted(allowed)[-1]})
+    except (AttributeError, OSError):
+        allowed = None
+    try:
+        return _cpu_reference_run_pinned(p, U, steps, warmup, budget_s, repeats, oracle)
+    finally:
+        if allowed is not None:
+            os.sched_setaffinity(0, allowed)
+
+
+def _cpu_reference_run_pinned(p, U, steps, warmup, budget_s, repeats, oracle):
     o = oracle.OracleSolver(p.M, U, tolerance=p.tol, smoother="gs", max_iter=100)
     t0 = time.perf_counter()
     o.solve(p.lhs, p.rhs)
