@@ -79,6 +79,7 @@ SIGNATURES = {
     "gmg_dist_unique_id": (C.c_int, [C.c_void_p, C.c_int64, _i64p]),
     "gmg_dist_init": (C.c_int, [_h, C.c_void_p, C.c_int64]),
     "gmg_dist_layout": (C.c_int, [_h, C.c_int64, _i32p, _i32p]),
+    "gmg_level_pattern": (C.c_int, [_h, C.c_int32, _i32p, _i32p, _i64p, _i64p]),
     "gmg_dist_windows": (C.c_int, [_h, C.c_int32, _i64p, _i64p, _i32p]),
     "gmg_dist_ranges": (C.c_int, [_h, C.c_int32, _i64p, _i32p]),
     "gmg_dist_halo": (C.c_int, [_h, C.c_int32, C.c_int32, C.c_int32, _i32p, _i64p, _i32p, _i64p]),

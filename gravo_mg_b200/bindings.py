@@ -388,6 +388,15 @@ class MultigridSolver:
         check(self._h, lib.gmg_dist_ranges(self._h, int(level), out.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(rep)))
         return out, bool(rep.value)
 
+    def level_pattern(self, level):
+        """Host only: (indptr, indices) of the operator pattern of ``level`` from the symbolic Galerkin phase."""
+        rows, nnz = C.c_int64(), C.c_int64()
+        check(self._h, lib.gmg_level_pattern(self._h, int(level), None, None, C.byref(rows), C.byref(nnz)))
+        indptr = np.empty(rows.value + 1, dtype=np.int32)
+        indices = np.empty(nnz.value, dtype=np.int32)
+        check(self._h, lib.gmg_level_pattern(self._h, int(level), i32(indptr), i32(indices), C.byref(rows), C.byref(nnz)))
+        return indptr, indices
+
     def dist_windows(self, which):
         """Row segments of the finest level this rank stores / uploads: ``which`` in 'A', 'U', 'Ut', 'rhs'.
         Returns (list of (begin, end), enabled)."""

@@ -555,6 +555,18 @@ int gmg_dist_layout(gmg_handle h, int64_t n, const int32_t* a_indptr, const int3
     });
 }
 
+int gmg_level_pattern(gmg_handle h, int32_t level, int32_t* indptr, int32_t* indices, int64_t* rows, int64_t* nnz) {
+    if (!h) return 1;
+    return guarded(h, [&] {
+        require(rows && nnz, "null argument");
+        require(level >= 0 && level < (int)h->s.a_pat.size(), "level out of range (call gmg_dist_layout or stage a system first)");
+        const gmg::HostCsr& m = h->s.a_pat[level];
+        *rows = m.rows, *nnz = m.nnz();
+        if (indptr) std::copy(m.indptr.begin(), m.indptr.end(), indptr);
+        if (indices) std::copy(m.indices.begin(), m.indices.end(), indices);
+    });
+}
+
 int gmg_dist_windows(gmg_handle h, int32_t which, int64_t* ranges, int64_t* count, int32_t* enabled) {
     if (!h) return 1;
     return guarded(h, [&] {

@@ -1,7 +1,10 @@
 #include "host_sparse.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <numeric>
+#include <thread>
 
 namespace gmg {
 
@@ -56,29 +59,53 @@ void sort_rows_sum_duplicates(HostCsr& a) {
     if (has_vals) a.data.resize(out);
 }
 
+// Worker threads of the symbolic products: GMG_HOST_THREADS, else min(8, hardware concurrency).
+static int host_threads() {
+    if (const char* e = std::getenv("GMG_HOST_THREADS")) return std::max(1, std::atoi(e));
+    return (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+}
+
+// Rows are independent (Gustavson with a per-thread marker array): contiguous row chunks on worker threads, the
+// per-chunk column lists concatenated in row order afterwards. Same output as the sequential loop for any thread count.
 HostCsr spgemm_symbolic(const HostCsr& a, const HostCsr& b) {
     HostCsr c;
     c.rows = a.rows;
     c.cols = b.cols;
     c.indptr.assign(c.rows + 1, 0);
-    std::vector<int> marker(b.cols, -1);
-    std::vector<int> rowbuf;
-    c.indices.reserve((size_t)a.nnz() * 2);
-    for (int64_t i = 0; i < a.rows; ++i) {
-        rowbuf.clear();
-        for (int p = a.indptr[i]; p < a.indptr[i + 1]; ++p) {
-            const int k = a.indices[p];
-            for (int q = b.indptr[k]; q < b.indptr[k + 1]; ++q) {
-                const int j = b.indices[q];
-                if (marker[j] != (int)i) {
-                    marker[j] = (int)i;
-                    rowbuf.push_back(j);
+    const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), a.rows / 8192 + 1));
+    std::vector<std::vector<int>> chunk_cols(n_threads);
+    auto work = [&](int t) {
+        const int64_t lo = a.rows * t / n_threads, hi = a.rows * (t + 1) / n_threads;
+        std::vector<int> marker(b.cols, -1);
+        std::vector<int> rowbuf;
+        std::vector<int>& out = chunk_cols[t];
+        out.reserve((size_t)(a.indptr[hi] - a.indptr[lo]) * 2);
+        for (int64_t i = lo; i < hi; ++i) {
+            rowbuf.clear();
+            for (int p = a.indptr[i]; p < a.indptr[i + 1]; ++p) {
+                const int k = a.indices[p];
+                for (int q = b.indptr[k]; q < b.indptr[k + 1]; ++q) {
+                    const int j = b.indices[q];
+                    if (marker[j] != (int)i) {
+                        marker[j] = (int)i;
+                        rowbuf.push_back(j);
+                    }
                 }
             }
+            std::sort(rowbuf.begin(), rowbuf.end());
+            out.insert(out.end(), rowbuf.begin(), rowbuf.end());
+            c.indptr[i + 1] = (int)rowbuf.size();  // row length for now
         }
-        std::sort(rowbuf.begin(), rowbuf.end());
-        c.indices.insert(c.indices.end(), rowbuf.begin(), rowbuf.end());
-        c.indptr[i + 1] = (int)c.indices.size();
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    for (int64_t i = 0; i < c.rows; ++i) c.indptr[i + 1] += c.indptr[i];
+    c.indices.resize((size_t)c.indptr[c.rows]);
+    for (int t = 0; t < n_threads; ++t) {
+        const int64_t lo = a.rows * t / n_threads;
+        if (!chunk_cols[t].empty()) std::memcpy(c.indices.data() + c.indptr[lo], chunk_cols[t].data(), chunk_cols[t].size() * sizeof(int));
     }
     return c;
 }

@@ -196,6 +196,9 @@ int gmg_dist_init(gmg_handle h, const void* id, int64_t size);
 /* Host-only: row ranges and halo lists for the given lhs pattern (what staging computes), so the
  * layout can be inspected and tested without a device. */
 int gmg_dist_layout(gmg_handle h, int64_t n, const int32_t* a_indptr, const int32_t* a_indices);
+/* Host only: sparsity pattern of the operator of a level as the symbolic Galerkin phase computed it (level 0: the lhs
+ * pattern; k >= 1: pattern of U^T A U, sorted columns). Query sizes with indptr == indices == NULL. */
+int gmg_level_pattern(gmg_handle h, int32_t level, int32_t* indptr, int32_t* indices, int64_t* rows, int64_t* nnz);
 /* Data decomposition of the finest level (after gmg_dist_layout or staging): the row segments this rank stores and
  * uploads per solve. which 0: rows of A_0 and A_0 U_0, 1: rows of U_0, 2: rows of U_0^T, 3: rows of the right-hand side.
  * ranges receives (begin, end) pairs; query the number of pairs with ranges == NULL. *enabled = 0: whole operators are

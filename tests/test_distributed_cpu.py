@@ -189,3 +189,31 @@ def test_finest_level_row_segments_hold_what_a_rank_reads(mesh, world):
     b.set_option("dist_window", 0)
     b.dist_layout(lhs)
     assert b.dist_windows("A")[1] is False
+
+
+@pytest.mark.parametrize("threads", ["1", "5"])
+def test_symbolic_galerkin_patterns_match_scipy(threads, monkeypatch):
+    """The host's symbolic products (threaded over row chunks, GMG_HOST_THREADS) give the patterns of U^T A U that
+    scipy computes, with sorted columns, for any thread count."""
+    import scipy.sparse as sp
+
+    import gravomg
+    from gravo_mg_b200 import synth
+
+    monkeypatch.setenv("GMG_HOST_THREADS", threads)
+    V, F = synth.torus_grid(150, 150)
+    V, S, M, neigh = synth.mesh_operators(V, F)
+    lhs, _ = synth.poisson_system(S, M)
+    solver = gravomg.MultigridSolver(V, neigh, M, lower_bound=100)
+    b = solver.solver
+    b.dist_configure(0, 1)
+    b.dist_layout(lhs)
+    cur = sp.csr_matrix((np.ones(lhs.nnz), lhs.indices, lhs.indptr), shape=lhs.shape)
+    for k, U in enumerate([u.tocsr() for u in solver.prolongation_matrices]):
+        Up = sp.csr_matrix((np.ones(U.nnz), U.indices, U.indptr), shape=U.shape)
+        cur = (Up.T @ cur @ Up).tocsr()
+        cur.sort_indices()
+        indptr, indices = b.level_pattern(k + 1)
+        np.testing.assert_array_equal(indptr, cur.indptr)
+        np.testing.assert_array_equal(indices, cur.indices)
+        cur.data[:] = 1.0
